@@ -1,0 +1,85 @@
+"""ctypes / numpy mirrors of include/focalsv_cuda.h (ABI version 1).
+
+Kept in one place so that the product binding (focalsv_b200.api), the oracle
+wrapper (oracle/oracle.py) and the tests all see the same layouts.
+"""
+import ctypes as C
+
+import numpy as np
+
+ABI_VERSION = 1
+NEG_INF = -0x40000000
+
+# ksw2.h:8-14
+EZ_SCORE_ONLY = 0x01
+EZ_RIGHT = 0x02
+EZ_GENERIC_SC = 0x04
+EZ_APPROX_MAX = 0x08
+EZ_APPROX_DROP = 0x10
+EZ_EXTZ_ONLY = 0x40
+EZ_REV_CIGAR = 0x80
+
+OK = 0
+ERR_NO_DEVICE = -1
+ERR_CUDA = -2
+ERR_INVALID = -3
+ERR_NOMEM = -4
+ERR_CIGAR_CAP = -5
+ERR_SCORING = -6
+ERR_STATE = -7
+
+
+class Scoring(C.Structure):
+    _fields_ = [("m", C.c_int8), ("q", C.c_int8), ("e", C.c_int8), ("q2", C.c_int8), ("e2", C.c_int8),
+                ("reserved", C.c_int8 * 3), ("mat", C.c_int8 * 32)]
+
+
+TASK_DTYPE = np.dtype([("q_off", "<i8"), ("t_off", "<i8"), ("qlen", "<i4"), ("tlen", "<i4"), ("w", "<i4"),
+                       ("zdrop", "<i4"), ("end_bonus", "<i4"), ("flag", "<i4")], align=True)
+RESULT_DTYPE = np.dtype([("max", "<i4"), ("zdropped", "<i4"), ("max_q", "<i4"), ("max_t", "<i4"),
+                         ("mqe", "<i4"), ("mqe_t", "<i4"), ("mte", "<i4"), ("mte_q", "<i4"),
+                         ("score", "<i4"), ("reach_end", "<i4"), ("n_cigar", "<i4"), ("status", "<i4"),
+                         ("cigar_off", "<i8"), ("cells", "<i8")], align=True)
+assert TASK_DTYPE.itemsize == 40 and RESULT_DTYPE.itemsize == 64
+
+# fields that must be bit-identical to ksw_extz_t (ksw2.h:23-32)
+EZ_FIELDS = ("max", "zdropped", "max_q", "max_t", "mqe", "mqe_t", "mte", "mte_q", "score", "reach_end", "n_cigar")
+
+
+class Stats(C.Structure):
+    _fields_ = [("tasks", C.c_int64), ("cells", C.c_int64), ("fill_launches", C.c_int64),
+                ("backtrack_launches", C.c_int64), ("other_launches", C.c_int64),
+                ("exact_path_tasks", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("fill_ms", C.c_double), ("backtrack_ms", C.c_double), ("total_ms", C.c_double),
+                ("traceback_bytes", C.c_int64)]
+
+
+def simple_mat(a, b, sc_ambi=1, m=5):
+    """5x5 matrix as minimap2's ksw_gen_simple_mat builds it: `a` on the diagonal,
+    -b elsewhere, -sc_ambi in the last row/column.  hifiasm's
+    call site uses 0 in the wildcard row/column (Correct.cpp:7670-7672)."""
+    a, b = abs(int(a)), abs(int(b))
+    mat = np.full((m, m), -b, dtype=np.int8)
+    for i in range(m - 1):
+        mat[i, i] = a
+    mat[m - 1, :] = -abs(int(sc_ambi))
+    mat[:, m - 1] = -abs(int(sc_ambi))
+    return mat.reshape(-1)
+
+
+def make_scoring(a, b, q, e, q2=-1, e2=-1, sc_ambi=1, m=5, mat=None):
+    sc = Scoring()
+    sc.m = m
+    sc.q, sc.e, sc.q2, sc.e2 = q, e, q2, e2
+    mm = simple_mat(a, b, sc_ambi, m) if mat is None else np.asarray(mat, dtype=np.int8).reshape(-1)
+    for i in range(m * m):
+        sc.mat[i] = int(mm[i])
+    return sc
+
+
+def scoring_mat(sc):
+    return np.array([sc.mat[i] for i in range(sc.m * sc.m)], dtype=np.int8)
+
+
+def cigar_str(words):
+    return "".join("%d%s" % (int(w) >> 4, "MIDNSHP=XB"[int(w) & 0xF]) for w in words)

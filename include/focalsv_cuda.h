@@ -1,0 +1,175 @@
+/*
+ * focalsv_cuda.h — C ABI of libfocalsv_cuda.so (B200 / sm_100a).
+ *
+ * Drop-in boundary for FocalSV's alignment-DP hot path.  Every entry point
+ * uses plain pointers and sizes only (no C++ / torch types) so it can be bound
+ * with ctypes from the reference's Python call sites:
+ *   focalsv/4_sv_calling/Dippav/DipPAV_variant_call.py:103-112   (asm5)
+ *   focalsv/TRA_INV_DUP_call/Target/call_DUP_from_contigs.py:114-126 (asm10)
+ *   focalsv/TRA_INV_DUP_call/Target/align_ins2ref.py:64-71      (map-hifi/pb/ont)
+ * and from C at the one in-tree native call site
+ *   software/hifiasm-0.16.1/Correct.cpp:7658-7705 (afine_gap_alignment).
+ *
+ * The arithmetic contract is the reference's ksw2:
+ *   software/hifiasm-0.16.1/ksw2.h:23-32   ksw_extz_t           -> fsv_result
+ *   software/hifiasm-0.16.1/ksw2.h:8-17    KSW_EZ_* flags       -> FSV_EZ_*
+ *   software/hifiasm-0.16.1/ksw2.h:54-55   ksw_extz2_sse(...)   -> fsv_ksw_extz2 / fsv_align_batch (q2<0)
+ *   software/hifiasm-0.16.1/ksw2.h:60-61   ksw_extd2_sse(...)   -> fsv_ksw_extd2 / fsv_align_batch
+ * Results (every fsv_result field and every CIGAR word) are bit-identical to
+ * those functions, including their band-rounding and tie-break behaviour.
+ *
+ * There is NO CPU fallback behind this ABI: without a CUDA device fsv_init
+ * fails with FSV_ERR_NO_DEVICE.
+ */
+#ifndef FOCALSV_CUDA_H_
+#define FOCALSV_CUDA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSV_ABI_VERSION 1
+
+/* ksw2.h:6 */
+#define FSV_NEG_INF (-0x40000000)
+
+/* ksw2.h:8-14 — same numeric values so reference flag words pass through. */
+#define FSV_EZ_SCORE_ONLY  0x01
+#define FSV_EZ_RIGHT       0x02
+#define FSV_EZ_GENERIC_SC  0x04
+#define FSV_EZ_APPROX_MAX  0x08
+#define FSV_EZ_APPROX_DROP 0x10
+#define FSV_EZ_EXTZ_ONLY   0x40
+#define FSV_EZ_REV_CIGAR   0x80
+
+/* error codes (0 = ok, negative = error; nothing ever aborts or throws) */
+enum {
+    FSV_OK = 0,
+    FSV_ERR_NO_DEVICE = -1,   /* no CUDA device / driver: there is no CPU path */
+    FSV_ERR_CUDA = -2,        /* a CUDA runtime call failed; see fsv_last_error */
+    FSV_ERR_INVALID = -3,     /* bad argument (null pointer, negative size, ...) */
+    FSV_ERR_NOMEM = -4,       /* device or host allocation failed */
+    FSV_ERR_CIGAR_CAP = -5,   /* cigar arena too small; *cigar_used = words needed */
+    FSV_ERR_SCORING = -6,     /* scoring outside the range ksw2's int8 lanes can hold */
+    FSV_ERR_STATE = -7        /* batch object used out of order */
+};
+
+/* Scoring of one batch.  Mirrors the (m, mat, q, e, q2, e2) arguments of
+ * ksw2.h:54-61.  mat is the m*m matrix in row-major order; only m = 5 is
+ * used by the reference (Correct.cpp:7670-7672).  q2 < 0 selects the
+ * single-affine recurrence (ksw_extz2_sse); q2 >= 0 the dual-affine one
+ * (ksw_extd2_sse). */
+typedef struct fsv_scoring {
+    int8_t m;
+    int8_t q, e;
+    int8_t q2, e2;
+    int8_t reserved[3];
+    int8_t mat[32];           /* first m*m entries used */
+} fsv_scoring;
+
+/* One (query segment, target segment) task.  Sequences are uint8 codes
+ * 0..m-1 (Correct.cpp:7676-7685 encoding: A,C,G,T -> 0..3, other -> 4)
+ * living in caller-owned arenas; offsets are in bytes. */
+typedef struct fsv_task {
+    int64_t q_off;            /* offset of query[0] in the query arena */
+    int64_t t_off;            /* offset of target[0] in the target arena */
+    int32_t qlen, tlen;
+    int32_t w;                /* band width, <0 = max(qlen,tlen) (ksw2_extz2_sse.c:72) */
+    int32_t zdrop;            /* <0 disables (ksw2.h:170) */
+    int32_t end_bonus;
+    int32_t flag;             /* FSV_EZ_* */
+} fsv_task;
+
+/* Field-for-field ksw_extz_t (ksw2.h:23-32) minus the owned pointer. */
+typedef struct fsv_result {
+    int32_t max;              /* ksw_extz_t.max (31-bit unsigned field) */
+    int32_t zdropped;
+    int32_t max_q, max_t;
+    int32_t mqe, mqe_t;
+    int32_t mte, mte_q;
+    int32_t score;
+    int32_t reach_end;
+    int32_t n_cigar;
+    int32_t status;           /* per-task: 0 ok, FSV_ERR_SCORING if it was reset like ksw2_extz2_sse.c:82 */
+    int64_t cigar_off;        /* index (uint32 words) of this task's CIGAR in the arena */
+    int64_t cells;            /* in-band DP cells actually processed: sum_r (en0-st0+1) */
+} fsv_result;
+
+typedef struct fsv_stats {
+    int64_t tasks;            /* tasks processed since init */
+    int64_t cells;            /* in-band cells since init */
+    int64_t fill_launches;    /* DP fill kernel launches */
+    int64_t backtrack_launches;
+    int64_t other_launches;   /* pack / scan / gather kernels */
+    int64_t exact_path_tasks; /* tasks re-run on the int8-exact kernel */
+    int64_t h2d_bytes, d2h_bytes;
+    double  fill_ms;          /* CUDA-event time of fill kernels (last run) */
+    double  backtrack_ms;     /* CUDA-event time of backtrack kernels (last run) */
+    double  total_ms;         /* CUDA-event time of the last fsv_batch_run */
+    int64_t traceback_bytes;  /* traceback bytes written by the last run */
+} fsv_stats;
+
+typedef struct fsv_ctx fsv_ctx;
+typedef struct fsv_batch fsv_batch;
+
+/* ---- context --------------------------------------------------------- */
+/* One context per device per host thread/process (thread-compatible, not
+ * thread-safe).  device < 0 selects the current CUDA device. */
+int fsv_init(int device, fsv_ctx** ctx);
+void fsv_destroy(fsv_ctx* ctx);
+const char* fsv_strerror(int code);
+const char* fsv_last_error(const fsv_ctx* ctx);
+int fsv_abi_version(void);
+int fsv_device_count(void);
+int fsv_get_stats(const fsv_ctx* ctx, fsv_stats* out);
+/* tunables: "traceback_budget_bytes", "force_exact" (1 = int8-exact kernel only),
+ * "fill_threads" ... returns FSV_ERR_INVALID for unknown keys */
+int fsv_set_option(fsv_ctx* ctx, const char* key, int64_t value);
+
+/* ---- one-call batch API (host buffers in, host buffers out) ----------
+ * Replaces a loop of ksw_extz2_sse / ksw_extd2_sse calls (ksw2.h:54-61).
+ * All buffers are caller-owned.  On FSV_ERR_CIGAR_CAP the fsv_result array is
+ * fully valid (n_cigar set) and *cigar_used holds the words required. */
+int fsv_align_batch(fsv_ctx* ctx, const fsv_scoring* sc,
+                    const uint8_t* query_arena, size_t query_bytes,
+                    const uint8_t* target_arena, size_t target_bytes,
+                    const fsv_task* tasks, size_t n_tasks,
+                    fsv_result* out,
+                    uint32_t* cigar_arena, size_t cigar_cap, size_t* cigar_used);
+
+/* ---- staged batch API (device-resident timing, double buffering) ------
+ * create = H2D of arenas + task table; run = kernels only, inputs resident
+ * in HBM; fetch = D2H of results + compact CIGAR arena. */
+int fsv_batch_create(fsv_ctx* ctx, const fsv_scoring* sc,
+                     const uint8_t* query_arena, size_t query_bytes,
+                     const uint8_t* target_arena, size_t target_bytes,
+                     const fsv_task* tasks, size_t n_tasks, fsv_batch** batch);
+int fsv_batch_run(fsv_batch* batch);
+int fsv_batch_fetch(fsv_batch* batch, fsv_result* out,
+                    uint32_t* cigar_arena, size_t cigar_cap, size_t* cigar_used);
+void fsv_batch_destroy(fsv_batch* batch);
+
+/* ---- single-task convenience, argument-for-argument ksw2.h:54-61 ------
+ * (km dropped; ez -> fsv_result + caller-owned cigar buffer). */
+int fsv_ksw_extz2(fsv_ctx* ctx, int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+                  int8_t m, const int8_t* mat, int8_t q, int8_t e, int w, int zdrop,
+                  int end_bonus, int flag, fsv_result* ez, uint32_t* cigar, int cigar_cap);
+int fsv_ksw_extd2(fsv_ctx* ctx, int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+                  int8_t m, const int8_t* mat, int8_t q, int8_t e, int8_t q2, int8_t e2, int w,
+                  int zdrop, int end_bonus, int flag, fsv_result* ez, uint32_t* cigar, int cigar_cap);
+
+/* ---- host-side helpers (no device work) ------------------------------ */
+/* In-band cell count of one task if it runs to completion:
+ * sum over r of (en0 - st0 + 1) with the bounds of ksw2_extz2_sse.c:102-110. */
+int64_t fsv_task_cells(int32_t qlen, int32_t tlen, int32_t w);
+/* Longest-processing-time-first binning of tasks over n_bins:
+ * bin_of[i] receives the bin of task i.  Deterministic. */
+int fsv_lpt_bins(const fsv_task* tasks, size_t n_tasks, int n_bins, int32_t* bin_of);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FOCALSV_CUDA_H_ */
