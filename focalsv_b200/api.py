@@ -1,0 +1,218 @@
+"""ctypes binding of libfocalsv_cuda.so (include/focalsv_cuda.h).
+
+This is the host-side mirror a FocalSV maintainer would call at the sites that
+shell out to minimap2 today (DipPAV_variant_call.py:103-112,
+call_DUP_from_contigs.py:114-126, align_ins2ref.py:64-71).  It fails loudly:
+a missing shared object or a missing CUDA device raises; there is no CPU path.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+from ._abi import RESULT_DTYPE, TASK_DTYPE, Scoring, Stats
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfocalsv_cuda.so")
+
+# every symbol include/focalsv_cuda.h declares
+EXPORTS = ("fsv_init", "fsv_destroy", "fsv_strerror", "fsv_last_error", "fsv_abi_version", "fsv_device_count",
+           "fsv_get_stats", "fsv_set_option", "fsv_align_batch", "fsv_batch_create", "fsv_batch_run",
+           "fsv_batch_fetch", "fsv_batch_destroy", "fsv_ksw_extz2", "fsv_ksw_extd2", "fsv_task_cells",
+           "fsv_lpt_bins")
+
+_lib = None
+
+
+class FsvError(RuntimeError):
+    def __init__(self, code, msg=""):
+        self.code = code
+        RuntimeError.__init__(self, "libfocalsv_cuda error %d: %s" % (code, msg))
+
+
+def load_library(path=None):
+    """Load the CUDA library.  Raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise FsvError(_abi.ERR_NO_DEVICE, "%s not built: run `python -m focalsv_b200.build` "
+                       "(or __graft_entry__.build()); there is no CPU fallback" % p)
+    lib = C.CDLL(p)
+    vp, i32, i64, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
+    lib.fsv_init.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.fsv_destroy.argtypes = [vp]
+    lib.fsv_destroy.restype = None
+    lib.fsv_strerror.argtypes = [C.c_int]
+    lib.fsv_strerror.restype = C.c_char_p
+    lib.fsv_last_error.argtypes = [vp]
+    lib.fsv_last_error.restype = C.c_char_p
+    lib.fsv_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.fsv_set_option.argtypes = [vp, C.c_char_p, i64]
+    lib.fsv_align_batch.argtypes = [vp, C.POINTER(Scoring), vp, sz, vp, sz, vp, sz, vp, vp, sz, C.POINTER(sz)]
+    lib.fsv_batch_create.argtypes = [vp, C.POINTER(Scoring), vp, sz, vp, sz, vp, sz, C.POINTER(vp)]
+    lib.fsv_batch_run.argtypes = [vp]
+    lib.fsv_batch_fetch.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
+    lib.fsv_batch_destroy.argtypes = [vp]
+    lib.fsv_batch_destroy.restype = None
+    lib.fsv_task_cells.argtypes = [i32, i32, i32]
+    lib.fsv_task_cells.restype = i64
+    lib.fsv_lpt_bins.argtypes = [vp, sz, C.c_int, vp]
+    if lib.fsv_abi_version() != _abi.ABI_VERSION:
+        raise FsvError(_abi.ERR_INVALID, "ABI version mismatch")
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def task_cells(qlen, tlen, w):
+    return int(load_library().fsv_task_cells(qlen, tlen, w))
+
+
+def lpt_bins(tasks, n_bins):
+    """Length-balanced bins of independent tasks: returns bin index per task."""
+    tasks = np.ascontiguousarray(tasks, dtype=TASK_DTYPE)
+    out = np.zeros(len(tasks), dtype=np.int32)
+    rc = load_library().fsv_lpt_bins(tasks.ctypes.data, len(tasks), int(n_bins), out.ctypes.data)
+    if rc != 0:
+        raise FsvError(rc, "fsv_lpt_bins")
+    return out
+
+
+def make_tasks(qlens, tlens, w, zdrop, end_bonus=0, flag=0, q_offs=None, t_offs=None):
+    """Task table for sequences stored back to back in two arenas."""
+    qlens = np.asarray(qlens, dtype=np.int64)
+    tlens = np.asarray(tlens, dtype=np.int64)
+    n = len(qlens)
+    t = np.zeros(n, dtype=TASK_DTYPE)
+    t["qlen"], t["tlen"] = qlens, tlens
+    t["q_off"] = np.concatenate([[0], np.cumsum(qlens)[:-1]]) if q_offs is None else q_offs
+    t["t_off"] = np.concatenate([[0], np.cumsum(tlens)[:-1]]) if t_offs is None else t_offs
+    t["w"], t["zdrop"], t["end_bonus"], t["flag"] = w, zdrop, end_bonus, flag
+    return t
+
+
+class Aligner(object):
+    """One context per device per process (the reference forks joblib workers; create it lazily in each)."""
+
+    def __init__(self, device=-1):
+        self._lib = load_library()
+        h = C.c_void_p()
+        rc = self._lib.fsv_init(int(device), C.byref(h))
+        if rc != 0:
+            raise FsvError(rc, self._lib.fsv_strerror(rc).decode())
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.fsv_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise FsvError(rc, "%s: %s (%s)" % (what, self._lib.fsv_strerror(rc).decode(),
+                                                self._lib.fsv_last_error(self._h).decode()))
+
+    def set_option(self, key, value):
+        self._check(self._lib.fsv_set_option(self._h, key.encode(), int(value)), "fsv_set_option")
+
+    def stats(self):
+        s = Stats()
+        self._check(self._lib.fsv_get_stats(self._h, C.byref(s)), "fsv_get_stats")
+        return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+    @staticmethod
+    def _arena(a):
+        a = np.ascontiguousarray(a, dtype=np.uint8)
+        return a
+
+    def align_batch(self, sc, qarena, tarena, tasks, cigar_cap=None):
+        """Host buffers in, host buffers out (H2D + kernels + D2H).  Returns (results, cigar_arena)."""
+        qarena, tarena = self._arena(qarena), self._arena(tarena)
+        tasks = np.ascontiguousarray(tasks, dtype=TASK_DTYPE)
+        n = len(tasks)
+        out = np.zeros(n, dtype=RESULT_DTYPE)
+        if cigar_cap is None:
+            with_c = (tasks["flag"] & _abi.EZ_SCORE_ONLY) == 0
+            cigar_cap = int((tasks["qlen"].astype(np.int64) + tasks["tlen"] + 2)[with_c].sum()) + 16
+        cig = np.zeros(max(int(cigar_cap), 1), dtype=np.uint32)
+        used = C.c_size_t(0)
+        rc = self._lib.fsv_align_batch(self._h, C.byref(sc), qarena.ctypes.data, qarena.size, tarena.ctypes.data,
+                                       tarena.size, tasks.ctypes.data, n, out.ctypes.data, cig.ctypes.data,
+                                       int(cigar_cap), C.byref(used))
+        if rc == _abi.ERR_CIGAR_CAP:
+            raise FsvError(rc, "cigar arena too small: need %d words" % used.value)
+        self._check(rc, "fsv_align_batch")
+        return out, cig[:used.value]
+
+    def batch(self, sc, qarena, tarena, tasks):
+        return Batch(self, sc, qarena, tarena, tasks)
+
+    def _single(self, dual, query, target, sc, w, zdrop, end_bonus, flag):
+        query, target = self._arena(query), self._arena(target)
+        tasks = make_tasks([len(query)], [len(target)], w, zdrop, end_bonus, flag)
+        if dual != (sc.q2 >= 0):
+            raise FsvError(_abi.ERR_INVALID, "scoring does not match the requested gap model")
+        res, cig = self.align_batch(sc, query, target, tasks)
+        return res[0], cig
+
+    def extz2(self, query, target, sc, w=-1, zdrop=-1, end_bonus=0, flag=0):
+        """ksw_extz2_sse (ksw2.h:54-55) on the GPU."""
+        return self._single(False, query, target, sc, w, zdrop, end_bonus, flag)
+
+    def extd2(self, query, target, sc, w=-1, zdrop=-1, end_bonus=0, flag=0):
+        """ksw_extd2_sse (ksw2.h:60-61) on the GPU."""
+        return self._single(True, query, target, sc, w, zdrop, end_bonus, flag)
+
+
+class Batch(object):
+    """Staged batch: create = H2D, run = kernels on HBM-resident inputs, fetch = D2H."""
+
+    def __init__(self, aligner, sc, qarena, tarena, tasks):
+        self._al = aligner
+        self._lib = aligner._lib
+        self.qarena, self.tarena = aligner._arena(qarena), aligner._arena(tarena)
+        self.tasks = np.ascontiguousarray(tasks, dtype=TASK_DTYPE)
+        self.sc = sc
+        h = C.c_void_p()
+        rc = self._lib.fsv_batch_create(aligner._h, C.byref(sc), self.qarena.ctypes.data, self.qarena.size,
+                                        self.tarena.ctypes.data, self.tarena.size, self.tasks.ctypes.data,
+                                        len(self.tasks), C.byref(h))
+        aligner._check(rc, "fsv_batch_create")
+        self._h = h
+
+    def run(self):
+        self._al._check(self._lib.fsv_batch_run(self._h), "fsv_batch_run")
+
+    def fetch(self, cigar_cap=None):
+        n = len(self.tasks)
+        out = np.zeros(n, dtype=RESULT_DTYPE)
+        if cigar_cap is None:
+            cigar_cap = int((self.tasks["qlen"].astype(np.int64) + self.tasks["tlen"] + 2).sum()) + 16
+        cig = np.zeros(max(int(cigar_cap), 1), dtype=np.uint32)
+        used = C.c_size_t(0)
+        rc = self._lib.fsv_batch_fetch(self._h, out.ctypes.data, cig.ctypes.data, int(cigar_cap), C.byref(used))
+        self._al._check(rc, "fsv_batch_fetch")
+        return out, cig[:used.value]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.fsv_batch_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+def task_cigar(res_row, cigar_arena):
+    o, n = int(res_row["cigar_off"]), int(res_row["n_cigar"])
+    return cigar_arena[o:o + n]

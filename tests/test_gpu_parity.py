@@ -1,0 +1,145 @@
+"""GPU parity proper: libfocalsv_cuda (through the C ABI) vs the CPU oracle, bit-exact.
+
+Integer/byte/index work: every ksw_extz_t field, every CIGAR word and the in-band
+cell count must be identical (no tolerance)."""
+import numpy as np
+import pytest
+
+from focalsv_b200 import _abi, synth
+from focalsv_b200.api import FsvError, make_tasks, task_cigar
+from util import compare_group, describe, random_case, same_result
+
+pytestmark = pytest.mark.gpu
+
+
+def _fuzz(O, al, seed, n, dual, max_len=400):
+    rng = np.random.default_rng(seed)
+    bad = []
+    for it in range(n):
+        c = random_case(rng, max_len=max_len, dual=dual)
+        fo = O.extd2 if dual else O.extz2
+        fg = al.extd2 if dual else al.extz2
+        r1, c1 = fo(c["q"], c["t"], c["sc"], w=c["w"], zdrop=c["zdrop"], end_bonus=c["end_bonus"], flag=c["flag"])
+        r2, c2 = fg(c["q"], c["t"], c["sc"], w=c["w"], zdrop=c["zdrop"], end_bonus=c["end_bonus"], flag=c["flag"])
+        if not same_result(r1, c1, r2, c2) or int(r1["cells"]) != int(r2["cells"]):
+            bad.append((it, len(c["q"]), len(c["t"]), c["w"], c["zdrop"], hex(c["flag"]), describe(r1, c1), describe(r2, c2)))
+    return bad
+
+
+def test_fuzz_single_affine_exact_kernel(oracle, aligner):
+    aligner.set_option("force_exact", 1)
+    try:
+        bad = _fuzz(oracle, aligner, 11, 250, dual=False)
+    finally:
+        aligner.set_option("force_exact", 0)
+    assert not bad, bad[:3]
+
+
+def test_fuzz_dual_affine_exact_kernel(oracle, aligner):
+    aligner.set_option("force_exact", 1)
+    try:
+        bad = _fuzz(oracle, aligner, 12, 250, dual=True)
+    finally:
+        aligner.set_option("force_exact", 0)
+    assert not bad, bad[:3]
+
+
+def test_fuzz_single_affine_default_routing(oracle, aligner):
+    bad = _fuzz(oracle, aligner, 13, 250, dual=False)
+    assert not bad, bad[:3]
+
+
+def test_fuzz_dual_affine_default_routing(oracle, aligner):
+    bad = _fuzz(oracle, aligner, 14, 250, dual=True)
+    assert not bad, bad[:3]
+
+
+@pytest.mark.parametrize("force_exact", [0, 1])
+def test_small_mixed_batches(oracle, aligner, force_exact):
+    aligner.set_option("force_exact", force_exact)
+    try:
+        for g in synth.small_mixed(seed=7, n=24):
+            bad, ores, gres = compare_group(oracle, aligner, g)
+            assert not bad, (g.name, bad[:5])
+    finally:
+        aligner.set_option("force_exact", 0)
+
+
+def test_edge_cases(oracle, aligner):
+    sc = _abi.make_scoring(2, 4, 4, 2, sc_ambi=0)
+    sd = _abi.make_scoring(1, 19, 39, 3, 81, 1)
+    one = np.array([2], dtype=np.uint8)
+    seq = np.random.default_rng(3).integers(0, 4, 77).astype(np.uint8)
+    for q, t in ((one, one), (one, seq), (seq, one), (seq, seq), (seq[:16], seq[:17]), (seq[:33], seq[:15])):
+        for w in (-1, 0, 1, 8):
+            for flag in (0, _abi.EZ_EXTZ_ONLY, _abi.EZ_SCORE_ONLY, _abi.EZ_RIGHT | _abi.EZ_REV_CIGAR):
+                r1, c1 = oracle.extz2(q, t, sc, w=w, zdrop=50, flag=flag)
+                r2, c2 = aligner.extz2(q, t, sc, w=w, zdrop=50, flag=flag)
+                assert same_result(r1, c1, r2, c2), (len(q), len(t), w, flag, describe(r1, c1), describe(r2, c2))
+                r1, c1 = oracle.extd2(q, t, sd, w=w, zdrop=50, flag=flag)
+                r2, c2 = aligner.extd2(q, t, sd, w=w, zdrop=50, flag=flag)
+                assert same_result(r1, c1, r2, c2), (len(q), len(t), w, flag, describe(r1, c1), describe(r2, c2))
+
+
+def test_empty_and_reset_tasks(oracle, aligner):
+    """ksw2's silent returns (ksw2_extz2_sse.c:57,82) come back as successful tasks with reset results."""
+    sc = _abi.make_scoring(2, 4, 4, 2, sc_ambi=0)
+    seq = np.arange(40, dtype=np.uint8) & 3
+    tasks = make_tasks([0, 40, 40], [40, 0, 40], 50, 100)
+    tasks["q_off"] = 0
+    tasks["t_off"] = 0
+    res, cig = aligner.align_batch(sc, seq, seq, tasks)
+    for i in (0, 1):
+        assert int(res[i]["score"]) == _abi.NEG_INF and int(res[i]["max"]) == 0 and int(res[i]["n_cigar"]) == 0
+        assert int(res[i]["max_t"]) == -1 and int(res[i]["mqe_t"]) == -1
+    assert _abi.cigar_str(task_cigar(res[2], cig)) == "40M"
+    # mismatch score that int8 lanes cannot represent: -min_sc > 2(q+e)  (:82)
+    bad_sc = _abi.make_scoring(1, 60, 4, 2, sc_ambi=0)
+    res, cig = aligner.align_batch(bad_sc, seq, seq, tasks[2:])
+    r1, _ = oracle.extz2(seq, seq, bad_sc, w=50, zdrop=100)
+    assert int(res[0]["score"]) == _abi.NEG_INF == int(r1["score"]) and int(res[0]["n_cigar"]) == 0
+    res, cig = aligner.align_batch(sc, seq, seq, tasks[:0])
+    assert len(res) == 0 and len(cig) == 0
+
+
+def test_cigar_arena_overflow_reports_required_size(aligner):
+    sc = _abi.make_scoring(2, 4, 4, 2, sc_ambi=0)
+    rng = np.random.default_rng(5)
+    t = rng.integers(0, 4, 300).astype(np.uint8)
+    q = synth.mutate(rng, t, 0.05, 0.03, 0.03)
+    tasks = make_tasks([len(q)], [len(t)], -1, -1)
+    with pytest.raises(FsvError) as ei:
+        aligner.align_batch(sc, q, t, tasks, cigar_cap=2)
+    assert ei.value.code == _abi.ERR_CIGAR_CAP
+
+
+def test_bad_offsets_rejected(aligner):
+    sc = _abi.make_scoring(2, 4, 4, 2, sc_ambi=0)
+    seq = np.zeros(10, dtype=np.uint8)
+    tasks = make_tasks([20], [10], -1, -1)
+    with pytest.raises(FsvError) as ei:
+        aligner.align_batch(sc, seq, seq, tasks)
+    assert ei.value.code == _abi.ERR_INVALID
+
+
+def test_staged_batch_equals_one_call(oracle, aligner):
+    g = synth.small_mixed(seed=9, n=12)[1]
+    res1, cig1 = aligner.align_batch(g.scoring, g.qarena, g.tarena, g.tasks)
+    b = aligner.batch(g.scoring, g.qarena, g.tarena, g.tasks)
+    b.run(); b.run()          # re-running a resident batch is idempotent
+    res2, cig2 = b.fetch()
+    b.close()
+    for f in _abi.EZ_FIELDS:
+        assert np.array_equal(res1[f], res2[f])
+    for i in range(len(res1)):
+        assert np.array_equal(task_cigar(res1[i], cig1), task_cigar(res2[i], cig2))
+
+
+def test_medium_tasks_band_3001(oracle, aligner):
+    """cfg2-shaped but short enough for the oracle: asm5, w=3001, 6-12 kb contigs with planted SVs."""
+    rng = np.random.default_rng(21)
+    pairs, regions = synth.contig_pairs(rng, [6000, 9000, 12000], 1.0 / 4000.0, 0.002, max_net=1300, max_sv=1200)
+    g = synth._pack("medium.asm5", "asm5", pairs, 3001, 200, regions=regions)
+    bad, ores, gres = compare_group(oracle, aligner, g)
+    assert not bad, bad
+    assert all(int(r["zdropped"]) == 0 for r in gres)
