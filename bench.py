@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py — alignment GCUPS / target regions per second of the FocalSV alignment-DP hot path.
+
+  python bench.py --gpus N --steps K --warmup W            # our CUDA arm (libfocalsv_cuda)
+  python bench.py --impl reference --gpus N --steps K ...   # the reference arm: CPU, host cores
+
+A "step" is one pass of the hot path (DP fill + CIGAR reconstruction) over one batch of
+synthetic input: BASELINE.json configs[1] = FocalSV auto mode, 5 000 SV-rich regions x 2
+haplotype contigs vs hg38-shaped windows, asm5 scoring, band 3001 (-r2k), z-drop 200
+(focalsv_b200/synth.py config2, seed 1002).  Multi-GPU = weak scaling: every rank owns a
+length-balanced (LPT) shard of N x 5 000 regions; regions are independent, so there is no
+collective on the data path (torch.distributed only provides the barrier and max-over-ranks).
+
+One JSON line on rank 0; see README / DESIGN.md §6 for the fields.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from focalsv_b200 import _abi, synth  # noqa: E402
+from focalsv_b200.presets import PRESETS, ksw_band  # noqa: E402
+
+# canonical integer lane-ops per in-band cell: exact max + traceback
+OPS_PER_CELL = {"extz2": 35, "extd2": 54}
+CONFIG_SEED = 1002
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--regions", type=int, default=int(os.environ.get("FSV_BENCH_REGIONS", 5000)),
+                    help="regions per GPU (configs[1] = 5000)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per reference step / baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--force-exact", action="store_true", help="use only the general int8-exact kernel")
+    return ap.parse_args()
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def build_shard(rank, world, regions_per_gpu):
+    """Region lengths of the whole job (world x regions_per_gpu), LPT-binned by estimated cells;
+    this rank synthesises only its own bin."""
+    rng = np.random.default_rng(CONFIG_SEED)
+    lens = synth.sample_quantiles(rng, synth.REGION_LEN_Q, regions_per_gpu * world)
+    if world > 1:
+        w = ksw_band(PRESETS["asm5"].bw)
+        est = (2 * lens - 1) * np.minimum(lens, w + 1)
+        order = np.argsort(-est, kind="stable")
+        load = np.zeros(world, dtype=np.int64)
+        mine = []
+        for i in order:                       # longest-processing-time-first
+            b = int(np.argmin(load))
+            load[b] += est[i]
+            if b == rank:
+                mine.append(i)
+        lens = lens[np.array(sorted(mine), dtype=np.int64)]
+    groups = synth.config2(seed=CONFIG_SEED + 7919 * rank, lens=lens)
+    return groups[0], len(lens)
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.proc, self.lines = gpu, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_sample(group, seconds, cores, gcups_guess):
+    """Bounded sample of the same workload: whole tasks, largest-first stride, ~`seconds` of CPU work."""
+    t = group.tasks
+    est = (t["qlen"].astype(np.int64) + t["tlen"] - 1) * np.minimum(np.minimum(t["qlen"], t["tlen"]), t["w"] + 1)
+    budget = seconds * cores * gcups_guess * 1e9
+    rng = np.random.default_rng(99)
+    pick, tot = [], 0
+    for i in rng.permutation(len(t)):
+        if est[i] > budget * 0.5 and pick:
+            continue
+        pick.append(int(i)); tot += int(est[i])
+        if tot >= budget or len(pick) >= 4 * cores:
+            if tot >= budget:
+                break
+    return np.array(sorted(pick), dtype=np.int64)
+
+
+def run_cpu(group, idx, threads):
+    """The oracle timed as the CPU baseline (the one place bench.py executes oracle/)."""
+    from oracle import oracle as O
+    sub = group.tasks[idx]
+    use_ref = O.have_reference() and group.scoring.q2 < 0
+    t0 = time.perf_counter()
+    res, _ = O.run_batch(group.scoring, group.qarena, group.tarena, sub, threads=threads, use_reference=use_ref)
+    dt = time.perf_counter() - t0
+    return int(res["cells"].sum()), dt, ("reference" if use_ref else "port")
+
+
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    group, n_regions = build_shard(0, 1, args.regions)
+    cores = os.cpu_count() or 1
+    idx = cpu_sample(group, args.cpu_seconds, cores, 0.12)
+    regions = len(set(group.region_of[idx].tolist()))
+    for _ in range(max(args.warmup, 0)):
+        run_cpu(group, idx[: max(1, len(idx) // 8)], cores)
+    cells, secs, kind = 0, 0.0, "port"
+    for _ in range(args.steps):
+        c, dt, kind = run_cpu(group, idx, cores)
+        cells += c; secs += dt
+    gcups = cells / secs / 1e9
+    sample = "%d of %d tasks of cfg2 (seed %d), %.3g cells/step" % (len(idx), len(group.tasks), CONFIG_SEED, cells / max(args.steps, 1))
+    line = {"impl": "reference", "metric": "alignment_gcups", "value": gcups, "unit": "GCUPS", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / max(args.steps, 1) * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+            "regions_per_s": regions * args.steps / secs,
+            "config": workload_config(args, world, n_regions),
+            "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "dual-affine ksw_extd2_sse is not in /root/reference (minimap2 2.24 dependency); the CPU arm is the "
+                    "oracle's plain-C restatement (gcc -O3 -msse4.1), one task per thread, all host threads"}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world, n_regions):
+    return {"workload": "BASELINE configs[1]: FocalSV auto mode, %d SV-rich regions x 2 haplotype contigs per GPU vs "
+                        "hg38-shaped windows, asm5 (a=1,b=19,q=39,e=3,q2=81,e2=1), band 3001, zdrop 200, global + CIGAR"
+                        % args.regions,
+            "regions_per_gpu": args.regions, "regions_this_rank": n_regions, "tasks_per_region": 2,
+            "seed": CONFIG_SEED, "sharding": "LPT bins by estimated cells, no collective", "world": world,
+            "l2_policy": "inputs+traceback per step far exceed the 126 MB L2 (traceback alone is >100 GB/step)"}
+
+
+def main():
+    args = parse_args()
+    rank, local_rank, world = dist_env()
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from focalsv_b200 import api
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (ours) needs a CUDA device: libfocalsv_cuda has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    group, n_regions = build_shard(rank, world, args.regions)
+    kind = "extd2" if group.scoring.q2 >= 0 else "extz2"
+    al = api.Aligner(local_rank)
+    if args.force_exact:
+        al.set_option("force_exact", 1)
+
+    # ---- device-resident arm: inputs in HBM before the clock starts
+    batch = al.batch(group.scoring, group.qarena, group.tarena, group.tasks)
+    for _ in range(args.warmup):
+        batch.run()
+    barrier()
+    st0 = al.stats()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    dev_ms = fill_ms = bt_ms = 0.0
+    for _ in range(args.steps):
+        batch.run()                       # kernels on the library's stream; it synchronises that stream
+        s = al.stats()
+        dev_ms += s["total_ms"]; fill_ms += s["fill_ms"]; bt_ms += s["backtrack_ms"]
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    st1 = al.stats()
+    res, cig = batch.fetch()
+    batch.close()
+    cells_step = int(res["cells"].sum())
+    dev_s = max_over_ranks(dev_ms * 1e-3)         # CUDA events on the launching stream, max over ranks
+    wall_s = max_over_ranks(wall)
+    tot_cells = sum_over_ranks(float(cells_step)) * args.steps
+    tot_regions = sum_over_ranks(float(n_regions)) * args.steps
+    gcups = tot_cells / dev_s / 1e9
+    launches = (st1["fill_launches"] + st1["backtrack_launches"] + st1["other_launches"]
+                - st0["fill_launches"] - st0["backtrack_launches"] - st0["other_launches"])
+
+    # ---- parity spot check of what was just timed (oracle as checker only)
+    parity = None
+    if rank == 0:
+        from oracle import oracle as O
+        small = np.argsort(group.tasks["qlen"].astype(np.int64) + group.tasks["tlen"])[:4]
+        ores, oarena = O.run_batch(group.scoring, group.qarena, group.tarena, group.tasks[small], threads=4)
+        ok = True
+        for k, i in enumerate(small):
+            gc = api.task_cigar(res[i], cig)
+            oc = oarena[int(ores[k]["cigar_off"]):int(ores[k]["cigar_off"]) + int(ores[k]["n_cigar"])]
+            ok &= all(int(res[i][f]) == int(ores[k][f]) for f in _abi.EZ_FIELDS) and np.array_equal(gc, oc)
+        parity = {"tasks_checked": int(len(small)), "bit_exact": bool(ok)}
+
+    # ---- end-to-end arm: host buffers through the public API, H2D and D2H inside the clock
+    e2e = None
+    if not args.no_e2e:
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
+        q_p, t_p = pin(group.qarena), pin(group.tarena)
+        tasks_p = pin(group.tasks.view(np.uint8)).view(_abi.TASK_DTYPE)
+        out_p = torch.empty(len(group.tasks) * _abi.RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory().numpy().view(_abi.RESULT_DTYPE)
+        cig_p = torch.empty(max(len(cig) + 1024, 1024), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+        al.align_batch(group.scoring, q_p, t_p, tasks_p, out=out_p, cig=cig_p)       # warm
+        barrier()
+        s0 = al.stats()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            r2, c2 = al.align_batch(group.scoring, q_p, t_p, tasks_p, out=out_p, cig=cig_p)
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        s1 = al.stats()
+        e2e = {"value": tot_cells / e2e_s / 1e9, "unit": "GCUPS",
+               "h2d_bytes_per_step": (s1["h2d_bytes"] - s0["h2d_bytes"]) // args.steps,
+               "d2h_bytes_per_step": (s1["d2h_bytes"] - s0["d2h_bytes"]) // args.steps,
+               "regions_per_s": tot_regions / e2e_s, "ms_per_step": e2e_s / args.steps * 1e3,
+               "timing": "host wall clock around fsv_align_batch (pinned host buffers; H2D + kernels + D2H), max over ranks"}
+
+    # ---- roofline of the dominant kernel (DP fill): integer issue rate, measured on this device
+    peaks = {}
+    names = {0: "VIADD.16x2", 1: "VIMNMX3.S16x2", 2: "VIADDMNMX.S16x2", 3: "LOP3", 4: "IMAD", 5: "fill-mix", 6: "PRMT", 7: "VIMNMX3+IMAD"}
+    for k, nm in names.items():
+        peaks[nm] = al.int_peak(k) / 1e12
+    peak = max(peaks.values())
+    fill_s = max_over_ranks(fill_ms * 1e-3)
+    achieved = cells_step * args.steps * OPS_PER_CELL[kind] / (fill_ms * 1e-3) / 1e12
+    hbm_peak = None
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            hbm_peak = json.load(fh).get("hbm_gbs")
+    except Exception:
+        pass
+    tb_gbs = st1["traceback_bytes"] * args.steps / (fill_ms * 1e-3) / 1e9
+    roofline = {"bound": "int_alu", "kernel": "fsv_fill (DP fill incl. traceback store)",
+                "achieved": achieved, "peak": peak, "unit": "Tlane-op/s", "frac": achieved / peak,
+                "ops_per_cell": OPS_PER_CELL[kind], "cells_per_launch": cells_step / max(1, (st1["fill_launches"] - st0["fill_launches"]) // max(args.steps, 1)),
+                "peak_source": "measured in this run (fsv_measure_int_peak), best of " + ", ".join("%s=%.1f" % kv for kv in sorted(peaks.items())),
+                "traffic": None,
+                "hbm": {"achieved": tb_gbs, "peak": hbm_peak or 6650.0, "unit": "GB/s",
+                        "frac": tb_gbs / (hbm_peak or 6650.0), "what": "traceback bytes written / fill time",
+                        "peak_source": "MEASURED_PEAKS.json" if hbm_peak else "fallback"},
+                "fill_share_of_step": fill_s / dev_s if dev_s else None,
+                "backtrack_ms_per_step": bt_ms / args.steps}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        idx = cpu_sample(group, args.cpu_seconds, cores, 0.12)
+        c, dt, knd = run_cpu(group, idx, cores)
+        cpu_baseline = {"value": c / dt / 1e9, "unit": "GCUPS", "cores": cores, "kind": knd,
+                        "sample": "%d of %d tasks (%.3g cells) of the same workload, one task per thread" % (len(idx), len(group.tasks), c),
+                        "seconds": dt}
+
+    if rank == 0:
+        line = {"metric": "alignment_gcups", "value": gcups, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+                "regions_per_s": tot_regions / dev_s, "wall_ms_per_step": wall_s / args.steps * 1e3,
+                "config": workload_config(args, world, n_regions), "clocks": clocks, "e2e": e2e,
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "parity": parity, "exact_path_tasks": int(st1["exact_path_tasks"] - st0["exact_path_tasks"]) // max(args.steps, 1),
+                "timing": "sum over steps of CUDA-event time on the library's launch stream, max over ranks"}
+        print(json.dumps(line), flush=True)
+    al.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

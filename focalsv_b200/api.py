@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(_HERE, "libfocalsv_cuda.so")
 EXPORTS = ("fsv_init", "fsv_destroy", "fsv_strerror", "fsv_last_error", "fsv_abi_version", "fsv_device_count",
            "fsv_get_stats", "fsv_set_option", "fsv_align_batch", "fsv_batch_create", "fsv_batch_run",
            "fsv_batch_fetch", "fsv_batch_destroy", "fsv_ksw_extz2", "fsv_ksw_extd2", "fsv_task_cells",
-           "fsv_lpt_bins")
+           "fsv_lpt_bins", "fsv_measure_int_peak")
 
 _lib = None
 
@@ -60,6 +60,7 @@ def load_library(path=None):
     lib.fsv_task_cells.argtypes = [i32, i32, i32]
     lib.fsv_task_cells.restype = i64
     lib.fsv_lpt_bins.argtypes = [vp, sz, C.c_int, vp]
+    lib.fsv_measure_int_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
     if lib.fsv_abi_version() != _abi.ABI_VERSION:
         raise FsvError(_abi.ERR_INVALID, "ABI version mismatch")
     if path is None:
@@ -131,21 +132,32 @@ class Aligner(object):
         self._check(self._lib.fsv_get_stats(self._h, C.byref(s)), "fsv_get_stats")
         return {k: getattr(s, k) for k, _ in Stats._fields_}
 
+    def int_peak(self, kind=5):
+        """Measured integer issue rate (lane-ops/s) of this device; see fsv_measure_int_peak."""
+        v = C.c_double(0)
+        self._check(self._lib.fsv_measure_int_peak(self._h, int(kind), C.byref(v)), "fsv_measure_int_peak")
+        return v.value
+
     @staticmethod
     def _arena(a):
         a = np.ascontiguousarray(a, dtype=np.uint8)
         return a
 
-    def align_batch(self, sc, qarena, tarena, tasks, cigar_cap=None):
-        """Host buffers in, host buffers out (H2D + kernels + D2H).  Returns (results, cigar_arena)."""
+    def align_batch(self, sc, qarena, tarena, tasks, cigar_cap=None, out=None, cig=None):
+        """Host buffers in, host buffers out (H2D + kernels + D2H).  Returns (results, cigar_arena).
+        `out` / `cig` may be caller-provided (e.g. pinned) buffers, as in the C ABI."""
         qarena, tarena = self._arena(qarena), self._arena(tarena)
         tasks = np.ascontiguousarray(tasks, dtype=TASK_DTYPE)
         n = len(tasks)
-        out = np.zeros(n, dtype=RESULT_DTYPE)
+        if out is None:
+            out = np.zeros(n, dtype=RESULT_DTYPE)
+        if cig is not None:
+            cigar_cap = len(cig)
         if cigar_cap is None:
             with_c = (tasks["flag"] & _abi.EZ_SCORE_ONLY) == 0
             cigar_cap = int((tasks["qlen"].astype(np.int64) + tasks["tlen"] + 2)[with_c].sum()) + 16
-        cig = np.zeros(max(int(cigar_cap), 1), dtype=np.uint32)
+        if cig is None:
+            cig = np.zeros(max(int(cigar_cap), 1), dtype=np.uint32)
         used = C.c_size_t(0)
         rc = self._lib.fsv_align_batch(self._h, C.byref(sc), qarena.ctypes.data, qarena.size, tarena.ctypes.data,
                                        tarena.size, tasks.ctypes.data, n, out.ctypes.data, cig.ctypes.data,

@@ -93,6 +93,8 @@ __global__ void __launch_bounds__(BT_THREADS) fsv_backtrack_kernel(const BtParam
             if (li < st) force = 2;
             if (li > en) force = 1;
             int cell = force < 0 ? tb[(int64_t)r * T.pitch + (li - st)] : 0;
+            // the DPX kernel stores the winner's priority code (tb_mode - d) in bits 0-2
+            if (T.tb_mode && force < 0) cell = (cell & ~7) | (T.tb_mode - (cell & 7));
             ns = bt_next_state(state, cell, force);
         }
         unsigned cont = __ballot_sync(0xffffffffu, valid && ns == state);

@@ -20,6 +20,7 @@
 #include "fsv_common.cuh"
 #include "fsv_fill_dpx.cuh"
 #include "fsv_fill_exact.cuh"
+#include "fsv_peaks.cuh"
 
 using namespace fsv;
 
@@ -40,6 +41,18 @@ struct fsv_ctx {
 };
 
 struct Chunk { int32_t begin, end; int64_t tb_bytes; };
+struct DpxLaunch { int chunk, nw, with_tb, begin, count; };   // a slice of order_dpx for one kernel variant
+
+// any base code outside A,C,G,T (0..3)?  8 bytes at a time.
+static bool has_wildcard(const uint8_t* p, size_t n)
+{
+    size_t i = 0;
+    uint64_t acc = 0;
+    for (; i + 8 <= n; i += 8) { uint64_t x; memcpy(&x, p + i, 8); acc |= x; }
+    uint8_t tail = 0;
+    for (; i < n; ++i) tail |= p[i];
+    return ((acc & 0xfcfcfcfcfcfcfcfcull) | (uint64_t)(tail & 0xfc)) != 0;
+}
 
 struct fsv_batch {
     fsv_ctx* ctx = nullptr;
@@ -51,6 +64,7 @@ struct fsv_batch {
     std::vector<int32_t> order_all;   // processing order (largest first), chunked
     std::vector<int32_t> order_dpx;   // per chunk: tasks for the DPX kernel (same index space as order_all)
     std::vector<Chunk> chunks;
+    std::vector<DpxLaunch> dpx_launches;
     std::vector<uint8_t> is_dpx;      // per task
     int64_t cigar_cap_words = 0;
     int64_t ws_lanes = 0;
@@ -279,7 +293,15 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
         d.pitch = n_col * 16;
         d.cells_est = cells_estimate(t.qlen, t.tlen, w);
         if (!(t.flag & FSV_EZ_SCORE_ONLY)) cigar_words += (int64_t)t.qlen + t.tlen + 2;
-        b->is_dpx[i] = (!c->force_exact && dpx_supports(b->sc, d)) ? 1 : 0;
+        if (!c->force_exact) {
+            // the DPX kernel packs bases in 2 bits: a task with a wildcard base goes to the general kernel
+            const bool wild = has_wildcard(qarena + t.q_off, (size_t)t.qlen) || has_wildcard(tarena + t.t_off, (size_t)t.tlen);
+            if (dpx_supports(b->sc, d, wild)) {
+                b->is_dpx[i] = 1;
+                d.nw = dpx_class_of(dpx_warps_needed(d));
+                d.tb_mode = b->dual ? 4 : 2;
+            }
+        }
     }
     b->cigar_cap_words = cigar_words;
 
@@ -316,20 +338,32 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
         ch.end = (int32_t)n;
         if (ch.end > ch.begin) b->chunks.push_back(ch);
     }
-    // per chunk, split the order into the two kernels' work lists (kept in the same slots)
+    // per chunk, split the order into work lists: one per kernel variant (general; DPX by
+    // warps-per-task class and with/without traceback), each still largest-first
     b->order_exact.assign(n, -1); b->order_dpx.assign(n, -1);
     int64_t ws_need = 0;
-    for (auto& ch : b->chunks) {
+    for (size_t ci = 0; ci < b->chunks.size(); ++ci) {
+        auto& ch = b->chunks[ci];
         int ne = 0, nd = 0;
         for (int k = ch.begin; k < ch.end; ++k) {
             int ti = ord[k];
-            if (b->is_dpx[ti]) b->order_dpx[ch.begin + nd++] = ti;
-            else {
-                b->order_exact[ch.begin + ne++] = ti;
-                if (b->tasks[ti].kind == 1 && b->tasks[ti].pitch + 96 > c->exact_smem_lanes)
-                    ws_need = std::max<int64_t>(ws_need, b->tasks[ti].pitch + 96);
-            }
+            if (b->is_dpx[ti]) continue;
+            b->order_exact[ch.begin + ne++] = ti;
+            if (b->tasks[ti].kind == 1 && b->tasks[ti].pitch + 96 > c->exact_smem_lanes)
+                ws_need = std::max<int64_t>(ws_need, b->tasks[ti].pitch + 96);
         }
+        static const int kClasses[5] = {8, 6, 4, 2, 1};
+        for (int cls : kClasses)
+            for (int with_tb = 1; with_tb >= 0; --with_tb) {
+                int begin = ch.begin + nd;
+                for (int k = ch.begin; k < ch.end; ++k) {
+                    int ti = ord[k];
+                    if (!b->is_dpx[ti] || b->tasks[ti].nw != cls) continue;
+                    if ((int)!(b->tasks[ti].flag & FSV_EZ_SCORE_ONLY) != with_tb) continue;
+                    b->order_dpx[ch.begin + nd++] = ti;
+                }
+                if (ch.begin + nd > begin) b->dpx_launches.push_back(DpxLaunch{(int)ci, cls, with_tb, begin, ch.begin + nd - begin});
+            }
     }
     b->ws_lanes = ws_need ? pow2_at_least(ws_need) : 0;
 
@@ -426,17 +460,24 @@ extern "C" int fsv_batch_run(fsv_batch* b)
     CK(c, cudaMemsetAsync(b->d_counters, 0, 64, c->stream));
     CK(c, cudaEventRecord(e0, c->stream));
     int64_t tb_total = 0;
-    for (auto& ch : b->chunks) {
-        int n_exact = 0, n_dpx = 0;
-        for (int k = ch.begin; k < ch.end; ++k) { if (b->order_exact[k] >= 0) ++n_exact; if (b->order_dpx[k] >= 0) ++n_dpx; }
+    for (size_t ci = 0; ci < b->chunks.size(); ++ci) {
+        auto& ch = b->chunks[ci];
+        int n_exact = 0;
+        for (int k = ch.begin; k < ch.end; ++k) if (b->order_exact[k] >= 0) ++n_exact;
         cudaEvent_t a, m, z;
         CK(c, cudaEventCreate(&a)); CK(c, cudaEventCreate(&m)); CK(c, cudaEventCreate(&z));
         evs.push_back(a); evs.push_back(m); evs.push_back(z);
-        CK(c, cudaMemsetAsync(b->d_counters, 0, 8, c->stream));
+        CK(c, cudaMemsetAsync(b->d_counters, 0, 8, c->stream));          // [0] general-kernel cursor
+        CK(c, cudaMemsetAsync(b->d_counters + 4, 0, 48, c->stream));     // [4..15] one cursor per DPX launch
         CK(c, cudaEventRecord(a, c->stream));
-        if (n_dpx) {
-            rc = dpx_launch(c->stream, c->sm_count, b->sc, b->d_q, b->d_t, b->d_tasks, b->d_order_dpx + ch.begin, n_dpx,
-                            b->d_counters + 1, b->d_results, b->d_aux, c->d_tb, &c->last_error);
+        int slot = 4;
+        for (const DpxLaunch& L : b->dpx_launches) {
+            if (L.chunk != (int)ci) continue;
+            DpxParams D{};
+            D.qarena = b->d_q; D.tarena = b->d_t; D.tasks = b->d_tasks; D.order = b->d_order_dpx + L.begin;
+            D.n_order = L.count; D.counter = b->d_counters + slot++; D.results = b->d_results; D.aux = b->d_aux;
+            D.tb = c->d_tb; D.sc = b->sc;
+            rc = dpx_launch(c->stream, c->sm_count, b->dual, L.with_tb != 0, L.nw, D, &c->last_error);
             if (rc != FSV_OK) return rc;
             c->stats.fill_launches++;
         }
@@ -549,4 +590,49 @@ extern "C" int fsv_ksw_extd2(fsv_ctx* c, int qlen, const uint8_t* query, int tle
     sc.m = m; sc.q = q; sc.e = e; sc.q2 = q2; sc.e2 = e2;
     if (m > 0) memcpy(sc.mat, mat, (size_t)m * m);
     return single(c, sc, qlen, query, tlen, target, w, zdrop, end_bonus, flag, ez, cigar, cigar_cap);
+}
+
+// ---------------------------------------------------------------------------
+// roofline denominators measured on this device (see fsv_peaks.cuh)
+template <int KIND>
+static int run_peak(fsv_ctx* c, int iters, double* out)
+{
+    uint32_t* d = nullptr;
+    CK(c, cudaMalloc(&d, 4096));
+    int grid = c->sm_count * 8;
+    cudaEvent_t e0, e1;
+    CK(c, cudaEventCreate(&e0)); CK(c, cudaEventCreate(&e1));
+    fsv_peak_kernel<KIND><<<grid, 256, 0, c->stream>>>(d, iters / 8, 12345u);      // warm-up
+    double best = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+        CK(c, cudaEventRecord(e0, c->stream));
+        fsv_peak_kernel<KIND><<<grid, 256, 0, c->stream>>>(d, iters, 12345u + rep);
+        CK(c, cudaEventRecord(e1, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        float ms = 0;
+        CK(c, cudaEventElapsedTime(&ms, e0, e1));
+        double ops = (double)grid * 256.0 * (double)iters * PEAK_OPS_PER_ITER;
+        best = std::max(best, ops / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *out = best;
+    return FSV_OK;
+}
+
+extern "C" int fsv_measure_int_peak(fsv_ctx* c, int kind, double* lane_ops_per_s)
+{
+    if (!c || !lane_ops_per_s) return FSV_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    const int iters = 4096;
+    switch (kind) {
+        case 0: return run_peak<0>(c, iters, lane_ops_per_s);
+        case 1: return run_peak<1>(c, iters, lane_ops_per_s);
+        case 2: return run_peak<2>(c, iters, lane_ops_per_s);
+        case 3: return run_peak<3>(c, iters, lane_ops_per_s);
+        case 4: return run_peak<4>(c, iters, lane_ops_per_s);
+        case 5: return run_peak<5>(c, iters, lane_ops_per_s);
+        case 6: return run_peak<6>(c, iters, lane_ops_per_s);
+        case 7: return run_peak<7>(c, iters, lane_ops_per_s);
+        default: return FSV_ERR_INVALID;
+    }
 }

@@ -25,7 +25,9 @@ struct DevTask {
     int32_t pitch;          // traceback bytes per antidiagonal = n_col_*16 (:75-76)
     int32_t orig;           // index in the caller's task array
     int32_t kind;           // 0 = reset result only (ksw2's silent returns), 1 = run
-    int32_t pad_;
+    int32_t pad_;           // kind 0: the status to report
+    int32_t tb_mode;        // traceback direction encoding: 0 = ksw2's d, n > 0 = (n - d) (DPX kernel)
+    int32_t nw;             // DPX kernel: warps per task (0 = general kernel)
 };
 
 // where the CIGAR walk of a task starts (ksw2_extz2_sse.c:292-301)

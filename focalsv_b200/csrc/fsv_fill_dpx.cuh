@@ -1,16 +1,479 @@
-// fsv_fill_dpx.cuh — register-resident DPX fill kernel (placeholder until the kernel lands).
+// fsv_fill_dpx.cuh — the FAST fill kernel: register-resident, DPX (16x2) arithmetic.
+//
+// Shape (B200 / sm_100a):
+//   * one thread == one 16-lane vector of the reference's SSE loop
+//     (software/hifiasm-0.16.1/ksw2_extz2_sse.c:151,174,200: `for (t = st_; t <= en_; ++t)`),
+//     so the reference's rounding of the band to 16-lane vectors (:116) maps onto
+//     whole threads and every lane it computes outside [st0,en0] is computed here too;
+//   * the vector's state u,v,x,y,(x2,y2),s lives in REGISTERS for the whole time the
+//     vector is inside the band (about 2w antidiagonals), as 8 packed 16x2 words per array:
+//     word k holds lanes (k, k+8) of the vector, so the "t-1" operand of word k is simply
+//     word k-1 (no shifting); only word 0 needs the neighbour thread (one shuffle);
+//   * every int8 lane of the reference is kept in the HIGH byte of a 16-bit half: 16-bit
+//     wrap-around == int8 wrap-around, 16-bit signed/unsigned compares == int8 compares,
+//     and the LOW byte is free to carry a priority code, so that one VIMNMX3.S16x2
+//     yields both max(...) and which operand won, with the reference's tie order;
+//   * the band slides by one lane every other antidiagonal: vectors are owned
+//     round-robin (vector V -> thread V mod NT); a thread whose vector leaves the band
+//     re-arms itself NT vectors further right;
+//   * per antidiagonal: one 16-byte traceback store per thread (coalesced 512 B per warp),
+//     one warp REDUX for the exact max, one CTA barrier pair when a task spans several warps.
+// Tasks it does not take (wildcard bases, KSW_EZ_GENERIC_SC / RIGHT / APPROX_MAX, bands
+// wider than 8 warps of vectors) go to the general kernel in fsv_fill_exact.cuh.
 #pragma once
 #include <string>
+
 #include "fsv_common.cuh"
 
 namespace fsv {
 
-inline bool dpx_supports(const DevScoring&, const DevTask&) { return false; }
+constexpr int DPX_MAX_WARPS = 8;
 
-inline int dpx_launch(cudaStream_t, int, const DevScoring&, const uint8_t*, const uint8_t*, const DevTask*,
-                      const int32_t*, int, int32_t*, fsv_result*, DevAux*, uint8_t*, std::string*)
+struct DpxParams {
+    const uint8_t* qarena;
+    const uint8_t* tarena;
+    const DevTask* tasks;
+    const int32_t* order;
+    int32_t n_order;
+    int32_t* counter;
+    fsv_result* results;
+    DevAux* aux;
+    uint8_t* tb;
+    DevScoring sc;
+};
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
 {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(s));
+    return d;
+}
+__device__ __forceinline__ uint32_t hi8(int v) { return ((uint32_t)v & 0xffu) << 8; }       // int8 -> high byte of a half
+__device__ __forceinline__ uint32_t both(uint32_t h) { return (h & 0xffffu) * 0x00010001u; } // same half twice
+__device__ __forceinline__ int sext16(uint32_t h) { return (int)(int16_t)(uint16_t)h; }
+
+// half `hf` (0 = low lanes 0..7, 1 = high lanes 8..15) of word (c & 7) <- v16
+__device__ __forceinline__ void set_cell(uint32_t (&A)[8], int c, uint32_t v16)
+{
+    const uint32_t m = (c & 8) ? 0xffff0000u : 0x0000ffffu, val = both(v16);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (k == (c & 7)) A[k] = (A[k] & ~m) | (val & m);
+}
+__device__ __forceinline__ uint32_t get_cell(const uint32_t (&A)[8], int c)
+{
+    uint32_t w = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (k == (c & 7)) w = A[k];
+    return (c & 8) ? (w >> 16) : (w & 0xffffu);
+}
+// mask of the halves whose lane index c is in [lo, hi]
+__device__ __forceinline__ uint32_t lane_mask(int k, int lo, int hi)
+{
+    uint32_t m = 0;
+    if (k >= lo && k <= hi) m |= 0x0000ffffu;
+    if (k + 8 >= lo && k + 8 <= hi) m |= 0xffff0000u;
+    return m;
+}
+
+template <bool DUAL, bool TB, int NW>
+__global__ void __launch_bounds__(NW * 32) fsv_fill_dpx_kernel(const DpxParams P)
+{
+    constexpr int NT = NW * 32;
+    __shared__ int32_t sh_task;
+    __shared__ uint32_t sh_bx[2][NW], sh_bv[2][NW], sh_bx2[2][NW];   // lane 15 of each warp's last vector
+    __shared__ int32_t sh_bh[2][NW];                                   // ... and its H
+    __shared__ int32_t sh_mh[2][NW];                                   // per-warp max H
+    __shared__ uint32_t sh_mk[2][NW];                                  // per-warp best tie key
+    __shared__ int32_t sh_hen0[2], sh_hst0[2];                         // H[en0], H[st0]
+    const DevScoring& sc = P.sc;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned FULL = 0xffffffffu;
+
+    // ---- scoring constants in the "int8 in the high byte" format
+    const int qe = sc.q + sc.e, qe2 = sc.q2 + sc.e2;
+    // tie-break codes in the low byte (higher wins): left alignment, ksw2_extz2_sse.c:177-181
+    constexpr uint32_t cS = DUAL ? 4 : 2, cE = DUAL ? 3 : 1, cF = DUAL ? 2 : 0, cE2 = 1, cF2 = 0;
+    const uint32_t gU = both(DUAL ? hi8(-qe) : 0);                         // initial u, v (:84 / dual memset)
+    const uint32_t gX = both((DUAL ? hi8(-qe) : 0) | cE), gY = both((DUAL ? hi8(-qe) : 0) | cF);
+    const uint32_t gX2 = both(hi8(-qe2) | cE2), gY2 = both(hi8(-qe2) | cF2);
+    const uint32_t sInit = both((DUAL ? 0 : hi8(2 * qe)) | cS);            // s[] starts at 0 (kcalloc)
+    const uint32_t sMch = both((DUAL ? hi8(sc.sc_mch) : hi8(sc.sc_mch + 2 * qe)) | cS);
+    const uint32_t sMis = both((DUAL ? hi8(sc.sc_mis) : hi8(sc.sc_mis + 2 * qe)) | cS);
+    const uint32_t kClamp = both(hi8(sc.max_sc_clamp));
+    const uint32_t kQ = both(hi8(sc.q)), kQ2 = both(hi8(sc.q2)), kQE = both(hi8(qe)), kQE2 = both(hi8(qe2));
+    const uint32_t fE = both(cE), fF = both(cF), fE2 = both(cE2), fF2 = both(cF2);      // max(.,0) floors
+    const uint32_t oE = both(0x0100u | cE), oF = both(0x0100u | cF), oE2 = both(0x0100u | cE2), oF2 = both(0x0100u | cF2);
+    const uint32_t extSel = DUAL ? 0xB391u : 0x4341u;                      // int8 (signed / unsigned) -> int16
+    const int bias = DUAL ? 0 : qe, r0_bias = DUAL ? qe : 2 * qe;
+    const uint32_t kBias = both((uint32_t)bias & 0xffffu);
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sh_task = atomicAdd(P.counter, 1);
+        __syncthreads();
+        const int slot = sh_task;
+        if (slot >= P.n_order) return;
+        const int ti = P.order[slot];
+        const DevTask T = P.tasks[ti];
+        const int qlen = T.qlen, tlen = T.tlen, w = T.w, flag = T.flag;
+        const uint8_t* query = P.qarena + T.q_off;
+        const uint8_t* target = P.tarena + T.t_off;
+        uint8_t* tb = TB ? P.tb + T.tb_off : nullptr;
+        const int n_diag = qlen + tlen - 1;
+
+        uint32_t U[8], V[8], X[8], Y[8], X2[8], Y2[8], S[8], Hr[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { U[k] = V[k] = X[k] = Y[k] = X2[k] = Y2[k] = S[k] = Hr[k] = 0; }
+        int32_t Hb = 0;
+        int Vt = tid - NT;          // forces the (re)arm path on the first antidiagonal
+        uint32_t tw = 0, qw = 0, qnext = 0;
+        EzState ez; ez.reset();
+        int64_t cells = 0;
+        int last_st = -1, last_en = -1;
+        int32_t nbH_keep = 0;       // H of lane base-1 as last seen while its vector was alive
+
+        for (int r = 0; r < n_diag; ++r) {
+            int st0, en0;
+            band_limits(r, qlen, tlen, w, st0, en0);
+            if (st0 > en0) { ez.zdropped = 1; break; }
+            const int st = round_st(st0), en = round_en(en0), st_ = st >> 4, en_ = en >> 4;
+            cells += en0 - st0 + 1;
+            const int par = r & 1, ppar = par ^ 1;
+
+            // ---- neighbour's lane 15 as it stood after the previous antidiagonal
+            uint32_t nbX = __shfl_up_sync(FULL, X[7], 1), nbV = __shfl_up_sync(FULL, V[7], 1);
+            uint32_t nbX2 = DUAL ? __shfl_up_sync(FULL, X2[7], 1) : 0;
+            int32_t nbH = __shfl_up_sync(FULL, Hb + sext16(Hr[7] >> 16), 1);
+            if (NW == 1) {
+                uint32_t a = __shfl_sync(FULL, X[7], 31), b = __shfl_sync(FULL, V[7], 31);
+                uint32_t c2 = DUAL ? __shfl_sync(FULL, X2[7], 31) : 0;
+                int32_t h = __shfl_sync(FULL, Hb + sext16(Hr[7] >> 16), 31);
+                if (lane == 0) { nbX = a; nbV = b; nbX2 = c2; nbH = h; }
+            } else if (lane == 0 && r > 0) {
+                const int pw = (warp + NW - 1) % NW;
+                nbX = sh_bx[ppar][pw]; nbV = sh_bv[ppar][pw]; nbX2 = sh_bx2[ppar][pw]; nbH = sh_bh[ppar][pw];
+            }
+
+            // ---- a vector that fell below the band re-arms NT vectors to the right
+            bool rearmed = false;
+            if (Vt < st_) {
+                Vt += NT;
+                while (Vt < st_) Vt += NT;
+                rearmed = true;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { U[k] = gU; V[k] = gU; X[k] = gX; Y[k] = gY; X2[k] = gX2; Y2[k] = gY2; S[k] = sInit; Hr[k] = 0; }
+                Hb = 0;
+                tw = 0; qw = 0;
+                const int base = Vt << 4;
+                for (int c = 0; c < 16; ++c) {
+                    const int t = base + c, j = r - t;
+                    uint32_t tbse = t < tlen ? target[t] : 0;
+                    uint32_t qbse = (j >= 0 && j < qlen) ? query[j] : 0;
+                    tw |= (tbse & 3u) << (2 * c);
+                    qw |= (qbse & 3u) << (2 * c);
+                }
+            }
+            const int base = Vt << 4;
+            // the H array of the reference keeps lane base-1 after its vector left the band (:231 reads it)
+            if (Vt - 1 >= (last_st >> 4)) nbH_keep = nbH;
+            if (!rearmed) qw = (qw << 2) | qnext;        // lane c now faces query[r - base - c]
+            {   // prefetch the base that enters at lane 0 on the next antidiagonal
+                const int j = r + 1 - base;
+                qnext = (j >= 0 && j < qlen) ? (uint32_t)(query[j] & 3u) : 0u;
+            }
+
+            const bool active = Vt >= st_ && Vt <= en_;
+            const int store_end = st0 + ((en0 - st0) >> 4) * 16 + 15;      // profile stores (:126-140)
+            const bool lo_edge = Vt == st_, hi_edge = Vt == en_;
+            uint32_t tbw[8];
+
+            // ---- score profile for the lanes the reference rewrites on this antidiagonal
+            if (Vt >= st_ && base <= store_end) {
+                const uint32_t xr = tw ^ qw, ne = xr | (xr >> 1);             // bit 2c set <=> lane c mismatches
+                const bool full = base >= st0 && base + 15 <= store_end;
+                const int lo = st0 - base, hi = store_end - base;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t sh = k < 4 ? (ne << (7 - 2 * k)) : (ne << (15 - 2 * k));
+                    const uint32_t mm = prmt(sh, 0u, k < 4 ? 0xAA88u : 0xBB99u);   // 0xffff per mismatching half
+                    const uint32_t sv = (mm & sMis) | (~mm & sMch);
+                    if (full) S[k] = sv;
+                    else { const uint32_t lm = lane_mask(k, lo, hi); S[k] = (sv & lm) | (S[k] & ~lm); }
+                }
+            }
+
+            int32_t habs = INT32_MIN;      // this thread's best H over its in-band lanes
+            uint32_t pm = 0;               // packed per-half max of Hr
+            if (active) {
+                // ---- operands of word 0: lane -1 is the neighbour's lane 15, lane 7 is our own word 7
+                uint32_t XT0 = prmt(nbX, X[7], 0x5432u), VT0 = prmt(nbV, V[7], 0x5432u);
+                uint32_t X2T0 = DUAL ? prmt(nbX2, X2[7], 0x5432u) : 0;
+                if (lo_edge) {                                              // carries (:118-122)
+                    uint32_t x1, v1, x21;
+                    if (st > 0) {
+                        if (st - 1 >= last_st && st - 1 <= last_en) { x1 = XT0 & 0xffffu; v1 = VT0 & 0xffffu; x21 = X2T0 & 0xffffu; }
+                        else { x1 = gX & 0xffffu; v1 = gU & 0xffffu; x21 = gX2 & 0xffffu; }
+                    } else {
+                        x1 = gX & 0xffffu; x21 = gX2 & 0xffffu;
+                        if (DUAL) v1 = hi8(r == 0 ? -qe : r < sc.long_thres ? -sc.e : r == sc.long_thres ? sc.long_diff : -sc.e2);
+                        else v1 = hi8(r ? sc.q : 0);
+                    }
+                    XT0 = (XT0 & 0xffff0000u) | x1; VT0 = (VT0 & 0xffff0000u) | v1; X2T0 = (X2T0 & 0xffff0000u) | x21;
+                    if (!DUAL) {   // _mm_cvtsi32_si128(int8_t) sign-extends a negative carry into lanes 1..3 (:146-147)
+                        if (x1 & 0x8000u) { X[0] = (X[0] & 0xffff0000u) | 0xff00u | cE; X[1] = (X[1] & 0xffff0000u) | 0xff00u | cE; X[2] = (X[2] & 0xffff0000u) | 0xff00u | cE; }
+                        if (v1 & 0x8000u) { V[0] = (V[0] & 0xffff0000u) | 0xff00u; V[1] = (V[1] & 0xffff0000u) | 0xff00u; V[2] = (V[2] & 0xffff0000u) | 0xff00u; }
+                    }
+                }
+                if (en >= r && (r >> 4) == Vt) {                            // first row (:123)
+                    uint32_t eu;
+                    if (DUAL) eu = hi8(r == 0 ? -qe : r < sc.long_thres ? -sc.e : r == sc.long_thres ? sc.long_diff : -sc.e2);
+                    else eu = hi8(r ? sc.q : 0);
+                    set_cell(U, r & 15, eu); set_cell(Y, r & 15, gY & 0xffffu);
+                    if (DUAL) set_cell(Y2, r & 15, gY2 & 0xffffu);
+                }
+                int32_t fix_prev = 0;      // H of lane en0-1 before this antidiagonal (for :231)
+                const int ce = en0 - base; // lane of en0 inside this vector (valid when hi_edge)
+                if (hi_edge && r > 0 && en0 > 0) fix_prev = ce > 0 ? sext16(get_cell(Hr, ce - 1)) : 0;
+
+                // ---- the recurrence (:26-47, :171-196), words 7..0 so that word k-1 is still "old"
+#pragma unroll
+                for (int k = 7; k >= 0; --k) {
+                    const uint32_t xt1 = k ? X[k - 1] : XT0, vt1 = k ? V[k - 1] : VT0, x2t1 = DUAL ? (k ? X2[k - 1] : X2T0) : 0;
+                    const uint32_t ut = U[k];
+                    uint32_t zc, code, a, b, a2 = 0, b2 = 0;
+                    a = __vadd2(xt1, vt1);
+                    b = __vadd2(Y[k], ut);
+                    if (DUAL) {
+                        a2 = __vadd2(x2t1, vt1);
+                        b2 = __vadd2(Y2[k], ut);
+                        const uint32_t zk = __vimax3_s16x2(__vimax3_s16x2(S[k], a, b), a2, b2);
+                        code = zk & 0x00070007u;
+                        zc = __vmins2(zk & 0xff00ff00u, kClamp);
+                    } else {
+                        const uint32_t t1 = __vmaxs2(S[k], a);                 // signed (:179)
+                        const uint32_t t2 = __vmaxs2(t1, b);                   // d = b > z (signed compare, :180)
+                        code = t2 & 0x00070007u;
+                        zc = __vminu2(__vmaxu2(t1 & 0xff00ff00u, b & 0xff00ff00u), kClamp);   // unsigned (:41-42)
+                    }
+                    U[k] = __vsub2(zc, vt1);
+                    V[k] = __vsub2(zc, ut);
+                    const uint32_t nt1 = __vsub2(kQ, zc);
+                    const uint32_t xa = __viaddmax_s16x2(a, nt1, fE), ya = __viaddmax_s16x2(b, nt1, fF);
+                    uint32_t fl;
+                    if (DUAL) {
+                        const uint32_t nt2 = __vsub2(kQ2, zc);
+                        const uint32_t xa2 = __viaddmax_s16x2(a2, nt2, fE2), ya2 = __viaddmax_s16x2(b2, nt2, fF2);
+                        X[k] = __vsub2(xa, kQE); Y[k] = __vsub2(ya, kQE);
+                        X2[k] = __vsub2(xa2, kQE2); Y2[k] = __vsub2(ya2, kQE2);
+                        if (TB) fl = __vmins2(xa, oE) + 2u * __vmins2(ya, oF) + 4u * __vmins2(xa2, oE2) + 8u * __vmins2(ya2, oF2);
+                    } else {
+                        X[k] = xa; Y[k] = ya;
+                        if (TB) fl = __vmins2(xa, oE) + 2u * __vmins2(ya, oF);
+                    }
+                    if (TB) tbw[k] = ((fl >> 5) & 0x00780078u) | code;
+                }
+                if (TB) {   // 16 traceback bytes, lane order, one coalesced 16-byte store (:195)
+                    const uint32_t a01 = prmt(tbw[0], tbw[1], 0x6240u), a23 = prmt(tbw[2], tbw[3], 0x6240u);
+                    const uint32_t a45 = prmt(tbw[4], tbw[5], 0x6240u), a67 = prmt(tbw[6], tbw[7], 0x6240u);
+                    uint4 o;
+                    o.x = prmt(a01, a23, 0x5410u); o.y = prmt(a45, a67, 0x5410u);
+                    o.z = prmt(a01, a23, 0x7632u); o.w = prmt(a45, a67, 0x7632u);
+                    *reinterpret_cast<uint4*>(tb + (int64_t)r * T.pitch + (base - st)) = o;
+                }
+
+                // ---- exact max bookkeeping (:224-260): H[t] += v[t] - qe ; H[en0] from its left neighbour
+                int32_t fixv = 0;
+                if (hi_edge) {
+                    if (r == 0) fixv = (DUAL ? (int)(int8_t)(V[0] >> 8) : (int)((V[0] >> 8) & 0xffu)) - r0_bias;      // H[0] (:262)
+                    else if (en0 > 0) {
+                        const uint32_t u16 = get_cell(U, ce);
+                        const int un = DUAL ? (int)(int8_t)(u16 >> 8) : (int)((u16 >> 8) & 0xffu);
+                        fixv = (ce > 0 ? fix_prev : nbH_keep) + un - bias;
+                    }
+                }
+                // lanes below st0 keep their last in-band H, as the reference's H[] does (:231 may read it back)
+                const int lo_h = st0 - base;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    uint32_t dv = prmt(V[k], 0u, extSel);
+                    if (!DUAL) dv = __vsub2(dv, kBias);
+                    if (lo_h > 0) dv &= lane_mask(k, lo_h, 15);
+                    Hr[k] = __vadd2(Hr[k], dv);
+                }
+                if (hi_edge) {
+                    if (r == 0) { Hb = fixv; Hr[0] = Hr[0] & 0xffff0000u; }
+                    else if (en0 > 0) {
+                        if (ce > 0) set_cell(Hr, ce, (uint32_t)fixv & 0xffffu);
+                        else { Hb = fixv; Hr[0] = Hr[0] & 0xffff0000u; }
+                    }
+                }
+                uint32_t Hm[8];
+                const int lo = st0 - base, hi = en0 - base;
+                const bool full = lo <= 0 && hi >= 15;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (full) Hm[k] = Hr[k];
+                    else { const uint32_t lm = lane_mask(k, lo, hi); Hm[k] = (Hr[k] & lm) | (0x80008000u & ~lm); }
+                }
+                pm = __vimax3_s16x2(__vimax3_s16x2(Hm[0], Hm[1], Hm[2]), __vimax3_s16x2(Hm[3], Hm[4], Hm[5]), __vmaxs2(Hm[6], Hm[7]));
+                const int mrel = max(sext16(pm), sext16(pm >> 16));
+                habs = Hb + mrel;
+                if ((r & 31) == 31) {   // keep the relative scores small
+                    Hb += mrel;
+                    const uint32_t d = both((uint32_t)mrel & 0xffffu);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) Hr[k] = __vsub2(Hr[k], d);
+                }
+                const bool want_en0 = en0 == tlen - 1, want_st0 = r - st0 == qlen - 1;
+                if (hi_edge && want_en0) sh_hen0[par] = Hb + sext16(get_cell(Hr, en0 - base));
+                if (lo_edge && want_st0) sh_hst0[par] = Hb + sext16(get_cell(Hr, st0 - base));
+            }
+            // lane 15 of every warp's last vector, for the next antidiagonal
+            if (NW > 1 && lane == 31) {
+                sh_bx[par][warp] = X[7]; sh_bv[par][warp] = V[7]; sh_bx2[par][warp] = DUAL ? X2[7] : 0;
+                sh_bh[par][warp] = Hb + sext16(Hr[7] >> 16);
+            }
+
+            // ---- max over the antidiagonal, then the reference's tie order (:231-260)
+            int32_t max_H = __reduce_max_sync(FULL, habs);
+            if (NW > 1) {
+                if (lane == 0) sh_mh[par][warp] = max_H;
+                __syncthreads();
+#pragma unroll
+                for (int i = 0; i < NW; ++i) max_H = max(max_H, sh_mh[par][i]);
+            } else __syncwarp();
+            // the argmax is only observable when it becomes the new maximum or can trigger the z-drop (ksw2.h:164-174)
+            const bool need_t = max_H > ez.max || (T.zdrop >= 0 && ez.max - max_H > T.zdrop);
+            int max_t = en0;
+            if (need_t) {
+                uint32_t key = 0xffffffffu;
+                if (active && habs == max_H) {
+                    // lanes of this vector that hold the maximum, as a 16-bit mask
+                    const uint32_t mv = both((uint32_t)(max_H - Hb) & 0xffffu);
+                    uint32_t ne = 0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) ne += __vminu2(Hr[k] ^ mv, 0x00010001u) << k;
+                    uint32_t eq = ~((ne & 0xffu) | ((ne >> 8) & 0xff00u)) & 0xffffu;
+                    const int lo = max(st0 - base, 0), hi = min(en0 - base, 15);
+                    eq &= (0xffffu << lo) & (0xffffu >> (15 - hi));
+                    // order of the reference's scan (:231-260): lane en0, then four strided classes
+                    // from st0 (first hit of each), then the scalar tail [en1, en0)
+                    const int en1 = st0 + (en0 - st0) / 4 * 4;
+                    if (hi_edge && ((eq >> (en0 - base)) & 1u)) key = 0;
+                    else {
+                        const int nb = min(max(en1 - base, 0), 16);          // lanes below en1
+                        const uint32_t body = eq & ((1u << nb) - 1u), tail = eq & ~((1u << nb) - 1u);
+                        const int sft = (base - st0) & 3;
+#pragma unroll
+                        for (int i = 3; i >= 0; --i) {
+                            const uint32_t m = body & (0x1111u << ((i - sft) & 3));
+                            if (m) key = 1u + ((uint32_t)i << 26) + (uint32_t)(base + __ffs(m) - 1);
+                        }
+                        if (!body && tail) key = 1u + (4u << 26) + (uint32_t)(base + __ffs(tail) - 1);
+                    }
+                }
+                uint32_t best_key = __reduce_min_sync(FULL, key);
+                if (NW > 1) {
+                    if (lane == 0) sh_mk[par][warp] = best_key;
+                    __syncthreads();
+#pragma unroll
+                    for (int i = 0; i < NW; ++i) best_key = min(best_key, sh_mk[par][i]);
+                }
+                max_t = best_key == 0 ? en0 : (int)((best_key - 1u) & ((1u << 26) - 1u));
+            }
+            int32_t h_last = FSV_NEG_INF;
+            if (en0 == tlen - 1) {
+                h_last = sh_hen0[par];
+                if (h_last > ez.mte) { ez.mte = h_last; ez.mte_q = r - en; }    // rounded en (:263-264)
+            }
+            if (r - st0 == qlen - 1) {
+                const int32_t h = sh_hst0[par];
+                if (h > ez.mqe) { ez.mqe = h; ez.mqe_t = st0; }
+            }
+            if (ez.apply_zdrop(max_H, r, max_t, T.zdrop, sc.e_drop)) break;
+            if (r == n_diag - 1 && en0 == tlen - 1) ez.score = h_last;          // H[tlen-1] (:268-269)
+            last_st = st; last_en = en;
+        }
+
+        if (tid == 0) {   // end point and result (:292-301)
+            DevAux A; A.i0 = -1; A.j0 = -1; A.n_cigar = 0; A.pad_ = 0;
+            int reach_end = 0;
+            if (TB) {
+                if (!ez.zdropped && !(flag & FSV_EZ_EXTZ_ONLY)) { A.i0 = tlen - 1; A.j0 = qlen - 1; }
+                else if (!ez.zdropped && (flag & FSV_EZ_EXTZ_ONLY) && ez.mqe + T.end_bonus > ez.max) {
+                    reach_end = 1; A.i0 = ez.mqe_t; A.j0 = qlen - 1;
+                } else if (ez.max_t >= 0 && ez.max_q >= 0) { A.i0 = ez.max_t; A.j0 = ez.max_q; }
+            }
+            fsv_result R;
+            R.max = ez.max; R.zdropped = ez.zdropped; R.max_q = ez.max_q; R.max_t = ez.max_t;
+            R.mqe = ez.mqe; R.mqe_t = ez.mqe_t; R.mte = ez.mte; R.mte_q = ez.mte_q; R.score = ez.score;
+            R.reach_end = reach_end; R.n_cigar = 0; R.status = 0; R.cigar_off = 0; R.cells = cells;
+            P.results[T.orig] = R;
+            P.aux[ti] = A;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+
+// warps a task needs: one thread per band vector plus the profile-overhang vector
+inline int dpx_warps_needed(const DevTask& t) { return (t.pitch / 16 + 1 + 31) / 32; }
+
+inline int dpx_class_of(int warps)
+{
+    if (warps <= 1) return 1;
+    if (warps <= 2) return 2;
+    if (warps <= 4) return 4;
+    if (warps <= 6) return 6;
+    if (warps <= 8) return 8;
+    return 0;
+}
+
+// `has_wild` = some base of the task is not A/C/G/T (code > 3)
+inline bool dpx_supports(const DevScoring& sc, const DevTask& t, bool has_wild)
+{
+    if (t.kind != 1 || has_wild) return false;
+    if (t.flag & (FSV_EZ_GENERIC_SC | FSV_EZ_RIGHT | FSV_EZ_APPROX_MAX | FSV_EZ_APPROX_DROP)) return false;
+    if (sc.m != 5) return false;
+    return dpx_class_of(dpx_warps_needed(t)) != 0;
+}
+
+template <bool DUAL, bool TB, int NW>
+inline int dpx_launch_one(cudaStream_t stream, int sm_count, const DpxParams& P, std::string* err)
+{
+    auto kern = fsv_fill_dpx_kernel<DUAL, TB, NW>;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, 0);
+    if (e != cudaSuccess) { if (err) *err = cudaGetErrorString(e); cudaGetLastError(); return FSV_ERR_CUDA; }
+    if (per_sm < 1) per_sm = 1;
+    int grid = std::min(P.n_order, sm_count * per_sm);
+    kern<<<grid, NW * 32, 0, stream>>>(P);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { if (err) *err = cudaGetErrorString(e); return FSV_ERR_CUDA; }
     return FSV_OK;
+}
+
+template <bool DUAL, bool TB>
+inline int dpx_launch_nw(cudaStream_t stream, int sm_count, int nw, const DpxParams& P, std::string* err)
+{
+    switch (nw) {
+        case 1: return dpx_launch_one<DUAL, TB, 1>(stream, sm_count, P, err);
+        case 2: return dpx_launch_one<DUAL, TB, 2>(stream, sm_count, P, err);
+        case 4: return dpx_launch_one<DUAL, TB, 4>(stream, sm_count, P, err);
+        case 6: return dpx_launch_one<DUAL, TB, 6>(stream, sm_count, P, err);
+        case 8: return dpx_launch_one<DUAL, TB, 8>(stream, sm_count, P, err);
+    }
+    return FSV_ERR_INVALID;
+}
+
+// one launch per (warps-per-task class, with/without traceback); `order` holds n tasks of that class
+inline int dpx_launch(cudaStream_t stream, int sm_count, bool dual, bool with_tb, int nw, const DpxParams& P, std::string* err)
+{
+    if (dual) return with_tb ? dpx_launch_nw<true, true>(stream, sm_count, nw, P, err) : dpx_launch_nw<true, false>(stream, sm_count, nw, P, err);
+    return with_tb ? dpx_launch_nw<false, true>(stream, sm_count, nw, P, err) : dpx_launch_nw<false, false>(stream, sm_count, nw, P, err);
 }
 
 }  // namespace fsv

@@ -141,10 +141,12 @@ def contig_pairs(rng, region_lens, sv_per_bp, err, max_net, max_sv=None, n_hap=2
     return pairs, regions
 
 
-def config2(n_regions=5000, seed=1002, max_region=None):
-    """cfg2: auto mode, ~5k SV-rich regions, HiFi contigs vs hg38-shaped reference, asm5, -r2k."""
+def config2(n_regions=5000, seed=1002, max_region=None, lens=None):
+    """cfg2: auto mode, ~5k SV-rich regions, HiFi contigs vs hg38-shaped reference, asm5, -r2k.
+    `lens` overrides the sampled region lengths (used by the multi-GPU sharding in bench.py)."""
     rng = np.random.default_rng(seed)
-    lens = sample_quantiles(rng, REGION_LEN_Q, n_regions, cap=max_region)
+    if lens is None:
+        lens = sample_quantiles(rng, REGION_LEN_Q, n_regions, cap=max_region)
     p = PRESETS["asm5"]
     w = ksw_band(p.bw)
     pairs, regions = contig_pairs(rng, lens, 1.0 / 15000.0, 0.001, max_net=w // 2 - 200, max_sv=w // 2 - 300)

@@ -161,6 +161,13 @@ int fsv_ksw_extd2(fsv_ctx* ctx, int qlen, const uint8_t* query, int tlen, const 
                   int8_t m, const int8_t* mat, int8_t q, int8_t e, int8_t q2, int8_t e2, int w,
                   int zdrop, int end_bonus, int flag, fsv_result* ez, uint32_t* cigar, int cigar_cap);
 
+/* ---- roofline denominator ---------------------------------------------
+ * Measured issue rate (32-bit lane-ops per second, whole device) of a dependency-free
+ * stream of the instruction class the fill kernels are built from:
+ * kind 0 VIADD.16x2, 1 VIMNMX3.S16x2, 2 VIADDMNMX.S16x2, 3 LOP3, 4 IMAD, 5 the fill
+ * kernel's mix, 6 PRMT, 7 VIMNMX3 + IMAD interleaved (both integer pipes). */
+int fsv_measure_int_peak(fsv_ctx* ctx, int kind, double* lane_ops_per_s);
+
 /* ---- host-side helpers (no device work) ------------------------------ */
 /* In-band cell count of one task if it runs to completion:
  * sum over r of (en0 - st0 + 1) with the bounds of ksw2_extz2_sse.c:102-110. */
