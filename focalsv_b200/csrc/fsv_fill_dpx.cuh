@@ -55,17 +55,20 @@ __device__ __forceinline__ int sext16(uint32_t h) { return (int)(int16_t)(uint16
 // half `hf` (0 = low lanes 0..7, 1 = high lanes 8..15) of word (c & 7) <- v16
 __device__ __forceinline__ void set_cell(uint32_t (&A)[8], int c, uint32_t v16)
 {
+    // branch-free on purpose: every word is rewritten with a static index, so the arrays stay in
+    // registers (an `if (k == c) A[k] = ...` chain is turned into a local-memory store by the compiler)
     const uint32_t m = (c & 8) ? 0xffff0000u : 0x0000ffffu, val = both(v16);
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-        if (k == (c & 7)) A[k] = (A[k] & ~m) | (val & m);
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t sel = (uint32_t)-(int)(k == (c & 7)) & m;
+        A[k] ^= (A[k] ^ val) & sel;
+    }
 }
 __device__ __forceinline__ uint32_t get_cell(const uint32_t (&A)[8], int c)
 {
     uint32_t w = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-        if (k == (c & 7)) w = A[k];
+    for (int k = 0; k < 8; ++k) w |= A[k] & (uint32_t)-(int)(k == (c & 7));
     return (c & 8) ? (w >> 16) : (w & 0xffffu);
 }
 // mask of the halves whose lane index c is in [lo, hi]
