@@ -92,41 +92,118 @@ __device__ __forceinline__ uint32_t word_mask(uint32_t bits, int k) { return prm
 // resident CTAs per SM the register budget is tuned for
 template <int NW> struct DpxOcc { static constexpr int value = NW == 1 ? 12 : NW == 2 ? 6 : NW == 4 ? 3 : 2; };
 
+// scoring constants in the "int8 in the high byte of a 16-bit half" format
+template <bool DUAL>
+struct DpxConst {
+    // tie-break codes in the low byte (higher wins): left alignment, ksw2_extz2_sse.c:177-181
+    static constexpr uint32_t cS = DUAL ? 4 : 2, cE = DUAL ? 3 : 1, cF = DUAL ? 2 : 0, cE2 = 1, cF2 = 0;
+    uint32_t gU, gX, gY, gX2, gY2, sInit, sMch, sMis, kClamp, kQ, kQ2, kQE, kQE2, kBias;
+    int qe, qe2, bias, r0_bias;
+    __device__ __forceinline__ explicit DpxConst(const DevScoring& sc)
+    {
+        qe = sc.q + sc.e; qe2 = sc.q2 + sc.e2;
+        gU = both(DUAL ? hi8(-qe) : 0);                                      // initial u, v (:84 / dual memset)
+        gX = both((DUAL ? hi8(-qe) : 0) | cE); gY = both((DUAL ? hi8(-qe) : 0) | cF);
+        gX2 = both(hi8(-qe2) | cE2); gY2 = both(hi8(-qe2) | cF2);
+        sInit = both((DUAL ? 0 : hi8(2 * qe)) | cS);                         // s[] starts at 0 (kcalloc)
+        sMch = both((DUAL ? hi8(sc.sc_mch) : hi8(sc.sc_mch + 2 * qe)) | cS);
+        sMis = both((DUAL ? hi8(sc.sc_mis) : hi8(sc.sc_mis + 2 * qe)) | cS);
+        kClamp = both(hi8(sc.max_sc_clamp));
+        kQ = both(hi8(sc.q)); kQ2 = both(hi8(sc.q2)); kQE = both(hi8(qe)); kQE2 = both(hi8(qe2));
+        bias = DUAL ? 0 : qe; r0_bias = DUAL ? qe : 2 * qe;
+        kBias = both((uint32_t)bias & 0xffffu);
+    }
+};
+
+// score profile of the 16 lanes of a vector from the 2-bit packed target / query windows (:125-140)
+template <bool DUAL>
+__device__ __forceinline__ void dpx_profile(uint32_t (&sv)[8], uint32_t tw, uint32_t qw, const DpxConst<DUAL>& K)
+{
+    const uint32_t xr = tw ^ qw, ne = xr | (xr >> 1);             // bit 2c set <=> lane c mismatches
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t sh = k < 4 ? (ne << (7 - 2 * k)) : (ne << (15 - 2 * k));
+        const uint32_t mm = prmt(sh, 0u, k < 4 ? 0xAA88u : 0xBB99u);   // 0xffff per mismatching half
+        sv[k] = (mm & K.sMis) | (~mm & K.sMch);
+    }
+}
+
+// The recurrence on the 16 lanes of one vector (:26-47, :171-196), words 7..0 so that word k-1 is
+// still "old" when word k reads it.  XT0/VT0/X2T0 are the t-1 operands of word 0.
+template <bool DUAL, bool TB>
+__device__ __forceinline__ void dpx_cells(uint32_t (&U)[8], uint32_t (&V)[8], uint32_t (&X)[8], uint32_t (&Y)[8],
+                                          uint32_t (&X2)[8], uint32_t (&Y2)[8], const uint32_t (&S)[8],
+                                          uint32_t XT0, uint32_t VT0, uint32_t X2T0, const DpxConst<DUAL>& K, uint4& tbo)
+{
+    using C = DpxConst<DUAL>;
+    const uint32_t fE = both(C::cE), fF = both(C::cF), fE2 = both(C::cE2), fF2 = both(C::cF2);      // max(.,0) floors
+    const uint32_t oE = both(0x0100u | C::cE), oF = both(0x0100u | C::cF), oE2 = both(0x0100u | C::cE2), oF2 = both(0x0100u | C::cF2);
+    uint32_t tbw[8];
+#pragma unroll
+    for (int k = 7; k >= 0; --k) {
+        const uint32_t xt1 = k ? X[k - 1] : XT0, vt1 = k ? V[k - 1] : VT0, x2t1 = DUAL ? (k ? X2[k - 1] : X2T0) : 0;
+        const uint32_t ut = U[k];
+        uint32_t zc, code, a, b, a2 = 0, b2 = 0;
+        a = __vadd2(xt1, vt1);
+        b = __vadd2(Y[k], ut);
+        if (DUAL) {
+            a2 = __vadd2(x2t1, vt1);
+            b2 = __vadd2(Y2[k], ut);
+            const uint32_t zk = __vimax3_s16x2(__vimax3_s16x2(S[k], a, b), a2, b2);
+            code = zk & 0x00070007u;
+            zc = __vmins2(zk & 0xff00ff00u, K.kClamp);
+        } else {
+            const uint32_t t1 = __vmaxs2(S[k], a);                 // signed (:179)
+            const uint32_t t2 = __vmaxs2(t1, b);                   // d = b > z (signed compare, :180)
+            code = t2 & 0x00070007u;
+            zc = __vminu2(__vmaxu2(t1 & 0xff00ff00u, b & 0xff00ff00u), K.kClamp);   // unsigned (:41-42)
+        }
+        U[k] = __vsub2(zc, vt1);
+        V[k] = __vsub2(zc, ut);
+        const uint32_t n1 = __vsub2(K.kQ, zc);
+        const uint32_t xa = __viaddmax_s16x2(a, n1, fE), ya = __viaddmax_s16x2(b, n1, fF);
+        uint32_t fl = 0;
+        if (DUAL) {
+            const uint32_t n2 = __vsub2(K.kQ2, zc);
+            const uint32_t xa2 = __viaddmax_s16x2(a2, n2, fE2), ya2 = __viaddmax_s16x2(b2, n2, fF2);
+            X[k] = __vsub2(xa, K.kQE); Y[k] = __vsub2(ya, K.kQE);
+            X2[k] = __vsub2(xa2, K.kQE2); Y2[k] = __vsub2(ya2, K.kQE2);
+            if (TB) fl = __vmins2(xa, oE) + 2u * __vmins2(ya, oF) + 4u * __vmins2(xa2, oE2) + 8u * __vmins2(ya2, oF2);
+        } else {
+            X[k] = xa; Y[k] = ya;
+            if (TB) fl = __vmins2(xa, oE) + 2u * __vmins2(ya, oF);
+        }
+        if (TB) tbw[k] = ((fl >> 5) & 0x00780078u) | code;
+    }
+    if (TB) {   // 16 traceback bytes in lane order (:195)
+        const uint32_t a01 = prmt(tbw[0], tbw[1], 0x6240u), a23 = prmt(tbw[2], tbw[3], 0x6240u);
+        const uint32_t a45 = prmt(tbw[4], tbw[5], 0x6240u), a67 = prmt(tbw[6], tbw[7], 0x6240u);
+        tbo.x = prmt(a01, a23, 0x5410u); tbo.y = prmt(a45, a67, 0x5410u);
+        tbo.z = prmt(a01, a23, 0x7632u); tbo.w = prmt(a45, a67, 0x7632u);
+    }
+}
+
 template <bool DUAL, bool TB, int NW>
 __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kernel(const DpxParams P)
 {
     constexpr int NT = NW * 32;
+    using C = DpxConst<DUAL>;
     __shared__ int32_t sh_task;
-    __shared__ uint32_t sh_bx[2][NW], sh_bv[2][NW], sh_bx2[2][NW];   // lane 15 of each warp's last vector
+    __shared__ uint32_t sh_bx[2][NW], sh_bv[2][NW], sh_bx2[2][NW], sh_bq[2][NW];   // lane 15 of each warp's last vector
     __shared__ int32_t sh_bh[2][NW];                                   // ... and its H
     __shared__ int32_t sh_mh[3][NW];                                   // per-warp max H, ring over 3 antidiagonals
     __shared__ uint32_t sh_key[3];                                     // best tie key of an antidiagonal
     __shared__ int32_t sh_hen0[3], sh_hst0[3];                         // H[en0], H[st0]
+    __shared__ int32_t sh_stop;                                        // z-drop seen by the bookkeeping warp
     const DevScoring& sc = P.sc;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
-
-    // ---- scoring constants in the "int8 in the high byte" format
-    const int qe = sc.q + sc.e, qe2 = sc.q2 + sc.e2;
-    // tie-break codes in the low byte (higher wins): left alignment, ksw2_extz2_sse.c:177-181
-    constexpr uint32_t cS = DUAL ? 4 : 2, cE = DUAL ? 3 : 1, cF = DUAL ? 2 : 0, cE2 = 1, cF2 = 0;
-    const uint32_t gU = both(DUAL ? hi8(-qe) : 0);                         // initial u, v (:84 / dual memset)
-    const uint32_t gX = both((DUAL ? hi8(-qe) : 0) | cE), gY = both((DUAL ? hi8(-qe) : 0) | cF);
-    const uint32_t gX2 = both(hi8(-qe2) | cE2), gY2 = both(hi8(-qe2) | cF2);
-    const uint32_t sInit = both((DUAL ? 0 : hi8(2 * qe)) | cS);            // s[] starts at 0 (kcalloc)
-    const uint32_t sMch = both((DUAL ? hi8(sc.sc_mch) : hi8(sc.sc_mch + 2 * qe)) | cS);
-    const uint32_t sMis = both((DUAL ? hi8(sc.sc_mis) : hi8(sc.sc_mis + 2 * qe)) | cS);
-    const uint32_t kClamp = both(hi8(sc.max_sc_clamp));
-    const uint32_t kQ = both(hi8(sc.q)), kQ2 = both(hi8(sc.q2)), kQE = both(hi8(qe)), kQE2 = both(hi8(qe2));
-    const uint32_t fE = both(cE), fF = both(cF), fE2 = both(cE2), fF2 = both(cF2);      // max(.,0) floors
-    const uint32_t oE = both(0x0100u | cE), oF = both(0x0100u | cF), oE2 = both(0x0100u | cE2), oF2 = both(0x0100u | cF2);
-    const uint32_t extSel = DUAL ? 0xB391u : 0x4341u;                      // int8 (signed / unsigned) -> int16
-    const int bias = DUAL ? 0 : qe, r0_bias = DUAL ? qe : 2 * qe;
-    const uint32_t kBias = both((uint32_t)bias & 0xffffu);
+    const DpxConst<DUAL> K(sc);
+    const uint32_t extSel = DUAL ? 0xB391u : 0x4341u;                  // int8 (signed / unsigned) -> int16
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) sh_task = atomicAdd(P.counter, 1);
+        if (tid == 0) { sh_task = atomicAdd(P.counter, 1); sh_stop = 0; }
         __syncthreads();
         const int slot = sh_task;
         if (slot >= P.n_order) return;
@@ -143,16 +220,17 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
         for (int k = 0; k < 8; ++k) { U[k] = V[k] = X[k] = Y[k] = X2[k] = Y2[k] = S[k] = Hr[k] = 0; }
         int32_t Hb = 0;
         int Vt = tid - NT;          // forces the (re)arm path on the first antidiagonal
-        uint32_t tw = 0, qw = 0, qnext = 0;
-        EzState ez; ez.reset();
+        uint32_t tw = 0, qw = 0;
+        EzState ez; ez.reset();     // complete only in warp 0 (the bookkeeping warp)
         int64_t cells = 0;
         int last_st = -1, last_en = -1;
         int32_t nbH_keep = 0;       // H of lane base-1 as last seen while its vector was alive
-        // The ksw_extz_t bookkeeping of antidiagonal d is finished two iterations later (d+2): its
-        // maximum crosses the CTA through shared memory behind the ONE barrier of iteration d, the
-        // tie-break key of the lanes holding that maximum behind the barrier of iteration d+1.
+        // The ksw_extz_t bookkeeping of antidiagonal d is finished two iterations later (d+2), by warp 0
+        // only: the maximum of d crosses the CTA through shared memory behind the ONE barrier of
+        // iteration d, the tie-break key of the lanes holding it behind the barrier of iteration d+1.
         int stop_r = n_diag;        // first antidiagonal that is not computed (band exhausted, :111)
         bool dropped = false;
+        int32_t maxrun = 0;         // ez.max as every warp can track it (running maximum, ksw2.h:164)
         int32_t M1 = 0, M2 = 0;     // max H of antidiagonals r-1, r-2
         bool nt1 = false, nt2 = false;   // was the argmax of r-1 / r-2 needed?
         int32_t habs_p = INT32_MIN; bool act_p = false; int st0p = 0, en0p = 0;   // this thread at r-1
@@ -165,40 +243,47 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
             // ---- neighbour's lane 15 as it stood after the previous antidiagonal
             uint32_t nbX = __shfl_up_sync(FULL, X[7], 1), nbV = __shfl_up_sync(FULL, V[7], 1);
             uint32_t nbX2 = DUAL ? __shfl_up_sync(FULL, X2[7], 1) : 0;
-            int32_t nbH = __shfl_up_sync(FULL, Hb + sext16(Hr[7] >> 16), 1);
+            uint32_t nbQ = __shfl_up_sync(FULL, qw, 1);
             if (NW == 1) {
                 uint32_t a = __shfl_sync(FULL, X[7], 31), b = __shfl_sync(FULL, V[7], 31);
-                uint32_t c2 = DUAL ? __shfl_sync(FULL, X2[7], 31) : 0;
-                int32_t h = __shfl_sync(FULL, Hb + sext16(Hr[7] >> 16), 31);
-                if (lane == 0) { nbX = a; nbV = b; nbX2 = c2; nbH = h; }
+                uint32_t c2 = DUAL ? __shfl_sync(FULL, X2[7], 31) : 0, q2 = __shfl_sync(FULL, qw, 31);
+                if (lane == 0) { nbX = a; nbV = b; nbX2 = c2; nbQ = q2; }
             } else if (lane == 0 && r > 0) {
                 const int pw = (warp + NW - 1) % NW;
-                nbX = sh_bx[ppar][pw]; nbV = sh_bv[ppar][pw]; nbX2 = sh_bx2[ppar][pw]; nbH = sh_bh[ppar][pw];
+                nbX = sh_bx[ppar][pw]; nbV = sh_bv[ppar][pw]; nbX2 = sh_bx2[ppar][pw]; nbQ = sh_bq[ppar][pw];
             }
 
-            // ---- (A) finish the bookkeeping of antidiagonal d = r-2 (ksw2_extz2_sse.c:262-269)
+            // ---- (A) antidiagonal d = r-2 is final: bookkeeping (ksw2_extz2_sse.c:262-269)
             if (r >= 2) {
+                if (sh_stop) { dropped = true; break; }
+                maxrun = max(maxrun, M2);
                 const int d = r - 2;
-                int st0d, en0d;
-                band_limits(d, qlen, tlen, w, st0d, en0d);
-                cells += en0d - st0d + 1;
-                int max_t = en0d;
-                if (nt2) {
-                    const uint32_t bk = sh_key[s3m2];
-                    if (bk != 0) max_t = (int)((bk - 1u) & ((1u << 26) - 1u));
+                if (warp == 0 && !dropped) {
+                    int st0d, en0d;
+                    band_limits(d, qlen, tlen, w, st0d, en0d);
+                    cells += en0d - st0d + 1;
+                    int max_t = en0d;
+                    if (nt2) {
+                        const uint32_t bk = sh_key[s3m2];
+                        if (bk != 0) max_t = (int)((bk - 1u) & ((1u << 26) - 1u));
+                    }
+                    int32_t h_last = FSV_NEG_INF;
+                    if (en0d == tlen - 1) {
+                        h_last = sh_hen0[s3m2];
+                        if (h_last > ez.mte) { ez.mte = h_last; ez.mte_q = d - round_en(en0d); }   // rounded en (:263-264)
+                    }
+                    if (d - st0d == qlen - 1) {
+                        const int32_t h = sh_hst0[s3m2];
+                        if (h > ez.mqe) { ez.mqe = h; ez.mqe_t = st0d; }
+                    }
+                    if (ez.apply_zdrop(M2, d, max_t, T.zdrop, sc.e_drop)) { dropped = true; if (lane == 0) sh_stop = 1; }
+                    else if (d == n_diag - 1 && en0d == tlen - 1) ez.score = h_last;            // H[tlen-1]
                 }
-                int32_t h_last = FSV_NEG_INF;
-                if (en0d == tlen - 1) {
-                    h_last = sh_hen0[s3m2];
-                    if (h_last > ez.mte) { ez.mte = h_last; ez.mte_q = d - round_en(en0d); }   // rounded en (:263-264)
+                if (d == stop_r - 1) {     // every computed antidiagonal is final
+                    if (NW > 1) __syncthreads(); else __syncwarp();
+                    if (sh_stop) dropped = true;
+                    break;
                 }
-                if (d - st0d == qlen - 1) {
-                    const int32_t h = sh_hst0[s3m2];
-                    if (h > ez.mqe) { ez.mqe = h; ez.mqe_t = st0d; }
-                }
-                if (ez.apply_zdrop(M2, d, max_t, T.zdrop, sc.e_drop)) { dropped = true; break; }
-                if (d == n_diag - 1 && en0d == tlen - 1) ez.score = h_last;                    // H[tlen-1]
-                if (d == stop_r - 1) break;
             }
             // ---- (B) antidiagonal r-1: its maximum, and (only if observable, ksw2.h:164-174) who holds it
             if (r >= 1 && r - 1 < stop_r) {
@@ -206,7 +291,8 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
 #pragma unroll
                 for (int i = 1; i < NW; ++i) m = max(m, sh_mh[s3m1][i]);
                 M1 = m;
-                nt1 = m > ez.max || (T.zdrop >= 0 && ez.max - m > T.zdrop);
+                const int32_t mr = max(maxrun, M2);      // ez.max once r-2 is accounted for
+                nt1 = m > mr || (T.zdrop >= 0 && mr - m > T.zdrop);
                 if (nt1 && act_p && habs_p == m) {
                     // lanes of this vector that hold the maximum, as a 16-bit mask
                     const int base = Vt << 4;
@@ -246,180 +332,25 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
             act_p = false;
             if (valid) {
                 const int st = round_st(st0), en = round_en(en0), st_ = st >> 4, en_ = en >> 4;
-                // a vector that fell below the band re-arms NT vectors to the right
-                bool rearmed = false;
-                if (Vt < st_) {
-                    Vt += NT;
-                    while (Vt < st_) Vt += NT;
-                    rearmed = true;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) { U[k] = gU; V[k] = gU; X[k] = gX; Y[k] = gY; X2[k] = gX2; Y2[k] = gY2; S[k] = sInit; Hr[k] = 0; }
-                    Hb = 0;
-                    tw = 0; qw = 0;
-                    const int nb = Vt << 4;
-                    for (int c = 0; c < 16; ++c) {
-                        const int t = nb + c, j = r - t;
-                        uint32_t tbse = t < tlen ? target[t] : 0;
-                        uint32_t qbse = (j >= 0 && j < qlen) ? query[j] : 0;
-                        tw |= (tbse & 3u) << (2 * c);
-                        qw |= (qbse & 3u) << (2 * c);
-                    }
-                }
-                const int base = Vt << 4;
-                // the H array of the reference keeps lane base-1 after its vector left the band (:231 reads it)
-                if (Vt - 1 >= (last_st >> 4)) nbH_keep = nbH;
-                if (!rearmed) qw = (qw << 2) | qnext;        // lane c now faces query[r - base - c]
-                {   // prefetch the base that enters at lane 0 on the next antidiagonal
-                    const int j = r + 1 - base;
-                    qnext = (j >= 0 && j < qlen) ? (uint32_t)(query[j] & 3u) : 0u;
-                }
-                const bool active = Vt >= st_ && Vt <= en_;
-                const int store_end = st0 + ((en0 - st0) >> 4) * 16 + 15;      // profile stores (:126-140)
-                const bool lo_edge = Vt == st_, hi_edge = Vt == en_;
-
-                // ---- score profile for the lanes the reference rewrites on this antidiagonal
-                if (Vt >= st_ && base <= store_end) {
-                    const uint32_t xr = tw ^ qw, ne = xr | (xr >> 1);             // bit 2c set <=> lane c mismatches
-                    uint32_t sv[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const uint32_t sh = k < 4 ? (ne << (7 - 2 * k)) : (ne << (15 - 2 * k));
-                        const uint32_t mm = prmt(sh, 0u, k < 4 ? 0xAA88u : 0xBB99u);   // 0xffff per mismatching half
-                        sv[k] = (mm & sMis) | (~mm & sMch);
-                    }
-                    if (base >= st0 && base + 15 <= store_end) {
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) S[k] = sv[k];
-                    } else {
-                        const uint32_t bits = lane_bits(st0 - base, store_end - base);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) { const uint32_t lm = word_mask(bits, k); S[k] = (sv[k] & lm) | (S[k] & ~lm); }
-                    }
-                }
-
                 int32_t habs = INT32_MIN;      // this thread's best H over its in-band lanes
-                if (active) {
-                    // ---- operands of word 0: lane -1 is the neighbour's lane 15, lane 7 is our own word 7
-                    uint32_t XT0 = prmt(nbX, X[7], 0x5432u), VT0 = prmt(nbV, V[7], 0x5432u);
-                    uint32_t X2T0 = DUAL ? prmt(nbX2, X2[7], 0x5432u) : 0;
-                    int32_t fix_prev = 0;      // H of lane en0-1 before this antidiagonal (for :231)
-                    const int ce = en0 - base; // lane of en0 inside this vector (valid when hi_edge)
-                    const bool top_row = en >= r && (r >> 4) == Vt;
-                    if (lo_edge || hi_edge || top_row) {
-                        if (lo_edge) {                                              // carries (:118-122)
-                            uint32_t x1, v1, x21;
-                            if (st > 0) {
-                                if (st - 1 >= last_st && st - 1 <= last_en) { x1 = XT0 & 0xffffu; v1 = VT0 & 0xffffu; x21 = X2T0 & 0xffffu; }
-                                else { x1 = gX & 0xffffu; v1 = gU & 0xffffu; x21 = gX2 & 0xffffu; }
-                            } else {
-                                x1 = gX & 0xffffu; x21 = gX2 & 0xffffu;
-                                if (DUAL) v1 = hi8(r == 0 ? -qe : r < sc.long_thres ? -sc.e : r == sc.long_thres ? sc.long_diff : -sc.e2);
-                                else v1 = hi8(r ? sc.q : 0);
-                            }
-                            XT0 = (XT0 & 0xffff0000u) | x1; VT0 = (VT0 & 0xffff0000u) | v1; X2T0 = (X2T0 & 0xffff0000u) | x21;
-                            if (!DUAL) {   // _mm_cvtsi32_si128(int8_t) sign-extends a negative carry into lanes 1..3 (:146-147)
-                                if (x1 & 0x8000u) { X[0] = (X[0] & 0xffff0000u) | 0xff00u | cE; X[1] = (X[1] & 0xffff0000u) | 0xff00u | cE; X[2] = (X[2] & 0xffff0000u) | 0xff00u | cE; }
-                                if (v1 & 0x8000u) { V[0] = (V[0] & 0xffff0000u) | 0xff00u; V[1] = (V[1] & 0xffff0000u) | 0xff00u; V[2] = (V[2] & 0xffff0000u) | 0xff00u; }
-                            }
-                        }
-                        if (top_row) {                                              // first row (:123)
-                            uint32_t eu;
-                            if (DUAL) eu = hi8(r == 0 ? -qe : r < sc.long_thres ? -sc.e : r == sc.long_thres ? sc.long_diff : -sc.e2);
-                            else eu = hi8(r ? sc.q : 0);
-                            set_cell(U, r & 15, eu); set_cell(Y, r & 15, gY & 0xffffu);
-                            if (DUAL) set_cell(Y2, r & 15, gY2 & 0xffffu);
-                        }
-                        if (hi_edge && r > 0 && en0 > 0) fix_prev = ce > 0 ? sext16(get_cell(Hr, ce - 1)) : 0;
-                    }
-
-                    // ---- the recurrence (:26-47, :171-196), words 7..0 so that word k-1 is still "old"
-                    uint32_t tbw[8];
+                // a warp whose 32 vectors all lie strictly inside the band takes the short path
+                const bool inner = Vt > st_ && Vt < en_;
+                if (__all_sync(FULL, inner)) {
+                    const int base = Vt << 4;
+                    qw = (qw << 2) | (nbQ >> 30);            // lane c now faces query[r - base - c]
+                    dpx_profile<DUAL>(S, tw, qw, K);
+                    const uint32_t XT0 = prmt(nbX, X[7], 0x5432u), VT0 = prmt(nbV, V[7], 0x5432u);
+                    const uint32_t X2T0 = DUAL ? prmt(nbX2, X2[7], 0x5432u) : 0;
+                    uint4 o;
+                    dpx_cells<DUAL, TB>(U, V, X, Y, X2, Y2, S, XT0, VT0, X2T0, K, o);
+                    if (TB) *reinterpret_cast<uint4*>(tb + (int64_t)r * T.pitch + (base - st)) = o;
 #pragma unroll
-                    for (int k = 7; k >= 0; --k) {
-                        const uint32_t xt1 = k ? X[k - 1] : XT0, vt1 = k ? V[k - 1] : VT0, x2t1 = DUAL ? (k ? X2[k - 1] : X2T0) : 0;
-                        const uint32_t ut = U[k];
-                        uint32_t zc, code, a, b, a2 = 0, b2 = 0;
-                        a = __vadd2(xt1, vt1);
-                        b = __vadd2(Y[k], ut);
-                        if (DUAL) {
-                            a2 = __vadd2(x2t1, vt1);
-                            b2 = __vadd2(Y2[k], ut);
-                            const uint32_t zk = __vimax3_s16x2(__vimax3_s16x2(S[k], a, b), a2, b2);
-                            code = zk & 0x00070007u;
-                            zc = __vmins2(zk & 0xff00ff00u, kClamp);
-                        } else {
-                            const uint32_t t1 = __vmaxs2(S[k], a);                 // signed (:179)
-                            const uint32_t t2 = __vmaxs2(t1, b);                   // d = b > z (signed compare, :180)
-                            code = t2 & 0x00070007u;
-                            zc = __vminu2(__vmaxu2(t1 & 0xff00ff00u, b & 0xff00ff00u), kClamp);   // unsigned (:41-42)
-                        }
-                        U[k] = __vsub2(zc, vt1);
-                        V[k] = __vsub2(zc, ut);
-                        const uint32_t nt1_ = __vsub2(kQ, zc);
-                        const uint32_t xa = __viaddmax_s16x2(a, nt1_, fE), ya = __viaddmax_s16x2(b, nt1_, fF);
-                        uint32_t fl = 0;
-                        if (DUAL) {
-                            const uint32_t nt2_ = __vsub2(kQ2, zc);
-                            const uint32_t xa2 = __viaddmax_s16x2(a2, nt2_, fE2), ya2 = __viaddmax_s16x2(b2, nt2_, fF2);
-                            X[k] = __vsub2(xa, kQE); Y[k] = __vsub2(ya, kQE);
-                            X2[k] = __vsub2(xa2, kQE2); Y2[k] = __vsub2(ya2, kQE2);
-                            if (TB) fl = __vmins2(xa, oE) + 2u * __vmins2(ya, oF) + 4u * __vmins2(xa2, oE2) + 8u * __vmins2(ya2, oF2);
-                        } else {
-                            X[k] = xa; Y[k] = ya;
-                            if (TB) fl = __vmins2(xa, oE) + 2u * __vmins2(ya, oF);
-                        }
-                        if (TB) tbw[k] = ((fl >> 5) & 0x00780078u) | code;
+                    for (int k = 0; k < 8; ++k) {            // H[t] += v[t] - qe (:239-241)
+                        uint32_t dv = prmt(V[k], 0u, extSel);
+                        if (!DUAL) dv = __vsub2(dv, K.kBias);
+                        Hr[k] = __vadd2(Hr[k], dv);
                     }
-                    if (TB) {   // 16 traceback bytes, lane order, one coalesced 16-byte store (:195)
-                        const uint32_t a01 = prmt(tbw[0], tbw[1], 0x6240u), a23 = prmt(tbw[2], tbw[3], 0x6240u);
-                        const uint32_t a45 = prmt(tbw[4], tbw[5], 0x6240u), a67 = prmt(tbw[6], tbw[7], 0x6240u);
-                        uint4 o;
-                        o.x = prmt(a01, a23, 0x5410u); o.y = prmt(a45, a67, 0x5410u);
-                        o.z = prmt(a01, a23, 0x7632u); o.w = prmt(a45, a67, 0x7632u);
-                        *reinterpret_cast<uint4*>(tb + (int64_t)r * T.pitch + (base - st)) = o;
-                    }
-
-                    // ---- exact max bookkeeping (:224-260): H[t] += v[t] - qe ; H[en0] from its left neighbour
-                    uint32_t pm;
-                    if (base >= st0 && Vt < en_) {                  // every lane inside the band, en0 further right
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            uint32_t dv = prmt(V[k], 0u, extSel);
-                            if (!DUAL) dv = __vsub2(dv, kBias);
-                            Hr[k] = __vadd2(Hr[k], dv);
-                        }
-                        pm = __vimax3_s16x2(__vimax3_s16x2(Hr[0], Hr[1], Hr[2]), __vimax3_s16x2(Hr[3], Hr[4], Hr[5]), __vmaxs2(Hr[6], Hr[7]));
-                    } else {
-                        int32_t fixv = 0;
-                        const bool fix = hi_edge && (r == 0 || en0 > 0);
-                        if (fix) {
-                            if (r == 0) fixv = (DUAL ? (int)(int8_t)(V[0] >> 8) : (int)((V[0] >> 8) & 0xffu)) - r0_bias;      // H[0] (:262)
-                            else {
-                                const uint32_t u16 = get_cell(U, ce);
-                                const int un = DUAL ? (int)(int8_t)(u16 >> 8) : (int)((u16 >> 8) & 0xffu);
-                                fixv = (ce > 0 ? fix_prev : nbH_keep) + un - bias;
-                            }
-                        }
-                        // lanes below st0 keep their last in-band H, as the reference's H[] does (:231 may read it back)
-                        const uint32_t upd = lane_bits(st0 - base, 15);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            uint32_t dv = prmt(V[k], 0u, extSel);
-                            if (!DUAL) dv = __vsub2(dv, kBias);
-                            Hr[k] = __vadd2(Hr[k], dv & word_mask(upd, k));
-                        }
-                        if (fix) {
-                            if (r == 0 || ce == 0) { Hb = fixv; Hr[0] = Hr[0] & 0xffff0000u; }
-                            else set_cell(Hr, ce, (uint32_t)fixv & 0xffffu);
-                        }
-                        const uint32_t inb = lane_bits(st0 - base, en0 - base);
-                        uint32_t Hm[8];
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) { const uint32_t lm = word_mask(inb, k); Hm[k] = (Hr[k] & lm) | (0x80008000u & ~lm); }
-                        pm = __vimax3_s16x2(__vimax3_s16x2(Hm[0], Hm[1], Hm[2]), __vimax3_s16x2(Hm[3], Hm[4], Hm[5]), __vmaxs2(Hm[6], Hm[7]));
-                        if (hi_edge && en0 == tlen - 1) sh_hen0[s3] = Hb + sext16(get_cell(Hr, en0 - base));
-                        if (lo_edge && r - st0 == qlen - 1) sh_hst0[s3] = Hb + sext16(get_cell(Hr, st0 - base));
-                    }
+                    const uint32_t pm = __vimax3_s16x2(__vimax3_s16x2(Hr[0], Hr[1], Hr[2]), __vimax3_s16x2(Hr[3], Hr[4], Hr[5]), __vmaxs2(Hr[6], Hr[7]));
                     const int mrel = max(sext16(pm), sext16(pm >> 16));
                     habs = Hb + mrel;
                     if ((r & 31) == 31) {   // keep the relative scores small
@@ -428,13 +359,127 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
 #pragma unroll
                         for (int k = 0; k < 8; ++k) Hr[k] = __vsub2(Hr[k], dd);
                     }
-                    // H[st0] when st0 is lane 0 of a vector that lies wholly inside the band
-                    if (base == st0 && Vt < en_ && r - st0 == qlen - 1) sh_hst0[s3] = Hb + sext16(Hr[0]);
+                    act_p = true;
+                } else {
+                    // ---- general path: band edges, first row, profile overhang, idle and re-arming vectors
+                    int32_t nbH = __shfl_up_sync(FULL, Hb + sext16(Hr[7] >> 16), 1);
+                    if (NW == 1) { int32_t h = __shfl_sync(FULL, Hb + sext16(Hr[7] >> 16), 31); if (lane == 0) nbH = h; }
+                    else if (lane == 0 && r > 0) nbH = sh_bh[ppar][(warp + NW - 1) % NW];
+                    bool rearmed = false;
+                    if (Vt < st_) {            // a vector that fell below the band re-arms NT vectors to the right
+                        Vt += NT;
+                        while (Vt < st_) Vt += NT;
+                        rearmed = true;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) { U[k] = K.gU; V[k] = K.gU; X[k] = K.gX; Y[k] = K.gY; X2[k] = K.gX2; Y2[k] = K.gY2; S[k] = K.sInit; Hr[k] = 0; }
+                        Hb = 0;
+                        tw = 0; qw = 0;
+                        const int nb = Vt << 4;
+                        for (int c = 0; c < 16; ++c) {
+                            const int t = nb + c, j = r - t;
+                            uint32_t tbse = t < tlen ? target[t] : 0;
+                            uint32_t qbse = (j >= 0 && j < qlen) ? query[j] : 0;
+                            tw |= (tbse & 3u) << (2 * c);
+                            qw |= (qbse & 3u) << (2 * c);
+                        }
+                    }
+                    const int base = Vt << 4;
+                    // the H array of the reference keeps lane base-1 after its vector left the band (:231 reads it)
+                    if (Vt - 1 >= (last_st >> 4)) nbH_keep = nbH;
+                    const bool active = Vt >= st_ && Vt <= en_;
+                    const bool lo_edge = Vt == st_, hi_edge = Vt == en_;
+                    if (!rearmed) {            // lane c now faces query[r - base - c]
+                        uint32_t q0 = nbQ >> 30;
+                        if (lo_edge) { const int j = r - base; q0 = (j >= 0 && j < qlen) ? (uint32_t)(query[j] & 3u) : 0u; }
+                        qw = (qw << 2) | q0;
+                    }
+                    const int store_end = st0 + ((en0 - st0) >> 4) * 16 + 15;      // profile stores (:126-140)
+                    if (Vt >= st_ && base <= store_end) {
+                        uint32_t sv[8];
+                        dpx_profile<DUAL>(sv, tw, qw, K);
+                        const uint32_t bits = lane_bits(st0 - base, store_end - base);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) { const uint32_t lm = word_mask(bits, k); S[k] = (sv[k] & lm) | (S[k] & ~lm); }
+                    }
+                    if (active) {
+                        // operands of word 0: lane -1 is the neighbour's lane 15, lane 7 is our own word 7
+                        uint32_t XT0 = prmt(nbX, X[7], 0x5432u), VT0 = prmt(nbV, V[7], 0x5432u);
+                        uint32_t X2T0 = DUAL ? prmt(nbX2, X2[7], 0x5432u) : 0;
+                        int32_t fix_prev = 0;      // H of lane en0-1 before this antidiagonal (for :231)
+                        const int ce = en0 - base; // lane of en0 inside this vector (valid when hi_edge)
+                        if (lo_edge) {                                              // carries (:118-122)
+                            uint32_t x1, v1, x21;
+                            if (st > 0) {
+                                if (st - 1 >= last_st && st - 1 <= last_en) { x1 = XT0 & 0xffffu; v1 = VT0 & 0xffffu; x21 = X2T0 & 0xffffu; }
+                                else { x1 = K.gX & 0xffffu; v1 = K.gU & 0xffffu; x21 = K.gX2 & 0xffffu; }
+                            } else {
+                                x1 = K.gX & 0xffffu; x21 = K.gX2 & 0xffffu;
+                                if (DUAL) v1 = hi8(r == 0 ? -K.qe : r < sc.long_thres ? -sc.e : r == sc.long_thres ? sc.long_diff : -sc.e2);
+                                else v1 = hi8(r ? sc.q : 0);
+                            }
+                            XT0 = (XT0 & 0xffff0000u) | x1; VT0 = (VT0 & 0xffff0000u) | v1; X2T0 = (X2T0 & 0xffff0000u) | x21;
+                            if (!DUAL) {   // _mm_cvtsi32_si128(int8_t) sign-extends a negative carry into lanes 1..3 (:146-147)
+                                if (x1 & 0x8000u) { X[0] = (X[0] & 0xffff0000u) | 0xff00u | C::cE; X[1] = (X[1] & 0xffff0000u) | 0xff00u | C::cE; X[2] = (X[2] & 0xffff0000u) | 0xff00u | C::cE; }
+                                if (v1 & 0x8000u) { V[0] = (V[0] & 0xffff0000u) | 0xff00u; V[1] = (V[1] & 0xffff0000u) | 0xff00u; V[2] = (V[2] & 0xffff0000u) | 0xff00u; }
+                            }
+                        }
+                        if (en >= r && (r >> 4) == Vt) {                            // first row (:123)
+                            uint32_t eu;
+                            if (DUAL) eu = hi8(r == 0 ? -K.qe : r < sc.long_thres ? -sc.e : r == sc.long_thres ? sc.long_diff : -sc.e2);
+                            else eu = hi8(r ? sc.q : 0);
+                            set_cell(U, r & 15, eu); set_cell(Y, r & 15, K.gY & 0xffffu);
+                            if (DUAL) set_cell(Y2, r & 15, K.gY2 & 0xffffu);
+                        }
+                        if (hi_edge && r > 0 && en0 > 0) fix_prev = ce > 0 ? sext16(get_cell(Hr, ce - 1)) : 0;
+
+                        uint4 o;
+                        dpx_cells<DUAL, TB>(U, V, X, Y, X2, Y2, S, XT0, VT0, X2T0, K, o);
+                        if (TB) *reinterpret_cast<uint4*>(tb + (int64_t)r * T.pitch + (base - st)) = o;
+
+                        // exact max bookkeeping (:224-260): H[t] += v[t] - qe ; H[en0] from its left neighbour
+                        int32_t fixv = 0;
+                        const bool fix = hi_edge && (r == 0 || en0 > 0);
+                        if (fix) {
+                            if (r == 0) fixv = (DUAL ? (int)(int8_t)(V[0] >> 8) : (int)((V[0] >> 8) & 0xffu)) - K.r0_bias;      // H[0] (:262)
+                            else {
+                                const uint32_t u16 = get_cell(U, ce);
+                                const int un = DUAL ? (int)(int8_t)(u16 >> 8) : (int)((u16 >> 8) & 0xffu);
+                                fixv = (ce > 0 ? fix_prev : nbH_keep) + un - K.bias;
+                            }
+                        }
+                        // lanes below st0 keep their last in-band H, as the reference's H[] does (:231 may read it back)
+                        const uint32_t upd = lane_bits(st0 - base, 15);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            uint32_t dv = prmt(V[k], 0u, extSel);
+                            if (!DUAL) dv = __vsub2(dv, K.kBias);
+                            Hr[k] = __vadd2(Hr[k], dv & word_mask(upd, k));
+                        }
+                        if (fix) {
+                            if (r == 0 || ce == 0) { Hb = fixv; Hr[0] = Hr[0] & 0xffff0000u; }
+                            else set_cell(Hr, ce, (uint32_t)fixv & 0xffffu);
+                        }
+                        const uint32_t inb = lane_bits(st0 - base, en0 - base);
+                        uint32_t pm = 0x80008000u;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) { const uint32_t lm = word_mask(inb, k); pm = __vmaxs2(pm, (Hr[k] & lm) | (0x80008000u & ~lm)); }
+                        if (hi_edge && en0 == tlen - 1) sh_hen0[s3] = Hb + sext16(get_cell(Hr, en0 - base));
+                        if (lo_edge && r - st0 == qlen - 1) sh_hst0[s3] = Hb + sext16(get_cell(Hr, st0 - base));
+                        const int mrel = max(sext16(pm), sext16(pm >> 16));
+                        habs = Hb + mrel;
+                        if ((r & 31) == 31) {   // keep the relative scores small
+                            Hb += mrel;
+                            const uint32_t dd = both((uint32_t)mrel & 0xffffu);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) Hr[k] = __vsub2(Hr[k], dd);
+                        }
+                        act_p = true;
+                    }
                 }
-                act_p = active; habs_p = habs; st0p = st0; en0p = en0;
+                habs_p = habs; st0p = st0; en0p = en0;
                 // lane 15 of every warp's last vector, for the next antidiagonal
                 if (NW > 1 && lane == 31) {
-                    sh_bx[par][warp] = X[7]; sh_bv[par][warp] = V[7]; sh_bx2[par][warp] = DUAL ? X2[7] : 0;
+                    sh_bx[par][warp] = X[7]; sh_bv[par][warp] = V[7]; sh_bx2[par][warp] = DUAL ? X2[7] : 0; sh_bq[par][warp] = qw;
                     sh_bh[par][warp] = Hb + sext16(Hr[7] >> 16);
                 }
                 const int32_t wmax = __reduce_max_sync(FULL, habs);
