@@ -52,23 +52,22 @@ __device__ __forceinline__ uint32_t hi8(int v) { return ((uint32_t)v & 0xffu) <<
 __device__ __forceinline__ uint32_t both(uint32_t h) { return (h & 0xffffu) * 0x00010001u; } // same half twice
 __device__ __forceinline__ int sext16(uint32_t h) { return (int)(int16_t)(uint16_t)h; }
 
-// half `hf` (0 = low lanes 0..7, 1 = high lanes 8..15) of word (c & 7) <- v16
+// Lane c of a vector lives in half (c >> 3) of word (c & 7).  Both accessors use static register
+// indices only (select trees), so the arrays stay in registers (an `if (k == c) A[k] = ...` chain
+// would be turned into a local-memory access by the compiler).
 __device__ __forceinline__ void set_cell(uint32_t (&A)[8], int c, uint32_t v16)
 {
-    // branch-free on purpose: every word is rewritten with a static index, so the arrays stay in
-    // registers (an `if (k == c) A[k] = ...` chain is turned into a local-memory store by the compiler)
-    const uint32_t m = (c & 8) ? 0xffff0000u : 0x0000ffffu, val = both(v16);
+    const int kk = c & 7;
+    const uint32_t keep = (c & 8) ? 0x0000ffffu : 0xffff0000u, val = both(v16) & ~keep;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const uint32_t sel = (uint32_t)-(int)(k == (c & 7)) & m;
-        A[k] ^= (A[k] ^ val) & sel;
-    }
+    for (int k = 0; k < 8; ++k) A[k] = (k == kk) ? ((A[k] & keep) | val) : A[k];
 }
 __device__ __forceinline__ uint32_t get_cell(const uint32_t (&A)[8], int c)
 {
-    uint32_t w = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) w |= A[k] & (uint32_t)-(int)(k == (c & 7));
+    const bool b0 = c & 1, b1 = c & 2, b2 = c & 4;
+    const uint32_t s0 = b0 ? A[1] : A[0], s1 = b0 ? A[3] : A[2], s2 = b0 ? A[5] : A[4], s3 = b0 ? A[7] : A[6];
+    const uint32_t t0 = b1 ? s1 : s0, t1 = b1 ? s3 : s2;
+    const uint32_t w = b2 ? t1 : t0;
     return (c & 8) ? (w >> 16) : (w & 0xffffu);
 }
 // mask of the halves whose lane index c is in [lo, hi]
@@ -194,7 +193,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
     __shared__ int32_t sh_mh[3][NW];                                   // per-warp max H, ring over 3 antidiagonals
     __shared__ uint32_t sh_key[3];                                     // best tie key of an antidiagonal
     __shared__ int32_t sh_hen0[3], sh_hst0[3];                         // H[en0], H[st0]
-    __shared__ int32_t sh_stop;                                        // z-drop seen by the bookkeeping warp
+    __shared__ int32_t sh_stop;                                        // iteration at which warp 0 saw the z-drop
     const DevScoring& sc = P.sc;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
@@ -203,7 +202,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) { sh_task = atomicAdd(P.counter, 1); sh_stop = 0; }
+        if (tid == 0) { sh_task = atomicAdd(P.counter, 1); sh_stop = INT32_MAX; }
         __syncthreads();
         const int slot = sh_task;
         if (slot >= P.n_order) return;
@@ -224,7 +223,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
         EzState ez; ez.reset();     // complete only in warp 0 (the bookkeeping warp)
         int64_t cells = 0;
         int last_st = -1, last_en = -1;
-        int32_t nbH_keep = 0;       // H of lane base-1 as last seen while its vector was alive
+        int32_t hprev_keep = 0;     // H[en0-1] as last seen while that lane was inside the band
         // The ksw_extz_t bookkeeping of antidiagonal d is finished two iterations later (d+2), by warp 0
         // only: the maximum of d crosses the CTA through shared memory behind the ONE barrier of
         // iteration d, the tie-break key of the lanes holding it behind the barrier of iteration d+1.
@@ -255,7 +254,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
 
             // ---- (A) antidiagonal d = r-2 is final: bookkeeping (ksw2_extz2_sse.c:262-269)
             if (r >= 2) {
-                if (sh_stop) { dropped = true; break; }
+                if (sh_stop < r) { dropped = true; break; }      // set during an EARLIER iteration: every thread agrees
                 maxrun = max(maxrun, M2);
                 const int d = r - 2;
                 if (warp == 0 && !dropped) {
@@ -276,12 +275,12 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                         const int32_t h = sh_hst0[s3m2];
                         if (h > ez.mqe) { ez.mqe = h; ez.mqe_t = st0d; }
                     }
-                    if (ez.apply_zdrop(M2, d, max_t, T.zdrop, sc.e_drop)) { dropped = true; if (lane == 0) sh_stop = 1; }
+                    if (ez.apply_zdrop(M2, d, max_t, T.zdrop, sc.e_drop)) { dropped = true; if (lane == 0) sh_stop = r; }
                     else if (d == n_diag - 1 && en0d == tlen - 1) ez.score = h_last;            // H[tlen-1]
                 }
                 if (d == stop_r - 1) {     // every computed antidiagonal is final
                     if (NW > 1) __syncthreads(); else __syncwarp();
-                    if (sh_stop) dropped = true;
+                    if (sh_stop <= r) dropped = true;
                     break;
                 }
             }
@@ -384,8 +383,6 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                         }
                     }
                     const int base = Vt << 4;
-                    // the H array of the reference keeps lane base-1 after its vector left the band (:231 reads it)
-                    if (Vt - 1 >= (last_st >> 4)) nbH_keep = nbH;
                     const bool active = Vt >= st_ && Vt <= en_;
                     const bool lo_edge = Vt == st_, hi_edge = Vt == en_;
                     if (!rearmed) {            // lane c now faces query[r - base - c]
@@ -430,7 +427,12 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                             set_cell(U, r & 15, eu); set_cell(Y, r & 15, K.gY & 0xffffu);
                             if (DUAL) set_cell(Y2, r & 15, K.gY2 & 0xffffu);
                         }
-                        if (hi_edge && r > 0 && en0 > 0) fix_prev = ce > 0 ? sext16(get_cell(Hr, ce - 1)) : 0;
+                        // H[en0-1] as the reference's H[] holds it (:231): the value of the previous antidiagonal
+                        // while that lane was inside the band, else the value it had when it left the band
+                        if (hi_edge && r > 0 && en0 > 0) {
+                            if (en0 - 1 >= st0p) hprev_keep = ce > 0 ? Hb + sext16(get_cell(Hr, ce - 1)) : nbH;
+                            fix_prev = hprev_keep;
+                        }
 
                         uint4 o;
                         dpx_cells<DUAL, TB>(U, V, X, Y, X2, Y2, S, XT0, VT0, X2T0, K, o);
@@ -444,20 +446,18 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                             else {
                                 const uint32_t u16 = get_cell(U, ce);
                                 const int un = DUAL ? (int)(int8_t)(u16 >> 8) : (int)((u16 >> 8) & 0xffu);
-                                fixv = (ce > 0 ? fix_prev : nbH_keep) + un - K.bias;
+                                fixv = fix_prev + un - K.bias;          // absolute
                             }
                         }
-                        // lanes below st0 keep their last in-band H, as the reference's H[] does (:231 may read it back)
-                        const uint32_t upd = lane_bits(st0 - base, 15);
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             uint32_t dv = prmt(V[k], 0u, extSel);
                             if (!DUAL) dv = __vsub2(dv, K.kBias);
-                            Hr[k] = __vadd2(Hr[k], dv & word_mask(upd, k));
+                            Hr[k] = __vadd2(Hr[k], dv);
                         }
                         if (fix) {
                             if (r == 0 || ce == 0) { Hb = fixv; Hr[0] = Hr[0] & 0xffff0000u; }
-                            else set_cell(Hr, ce, (uint32_t)fixv & 0xffffu);
+                            else set_cell(Hr, ce, (uint32_t)(fixv - Hb) & 0xffffu);
                         }
                         const uint32_t inb = lane_bits(st0 - base, en0 - base);
                         uint32_t pm = 0x80008000u;
