@@ -140,6 +140,73 @@ def test_medium_tasks_band_3001(oracle, aligner):
     rng = np.random.default_rng(21)
     pairs, regions = synth.contig_pairs(rng, [6000, 9000, 12000], 1.0 / 4000.0, 0.002, max_net=1300, max_sv=1200)
     g = synth._pack("medium.asm5", "asm5", pairs, 3001, 200, regions=regions)
+    before = aligner.stats()["exact_path_tasks"]
     bad, ores, gres = compare_group(oracle, aligner, g)
     assert not bad, bad
-    assert all(int(r["zdropped"]) == 0 for r in gres)
+    assert aligner.stats()["exact_path_tasks"] == before      # all of them ran on the DPX kernel
+
+
+def _golden(name):
+    import os
+    from test_oracle_golden import load
+    return load(name)
+
+
+@pytest.mark.parametrize("fname,dual", [("kat_extz2.npz", False), ("kat_extd2.npz", True)])
+def test_golden_vectors_on_gpu(aligner, fname, dual):
+    """tests/golden: outputs of the reference's own compiled ksw_extz2_sse / frozen dual-affine vectors."""
+    for c in _golden(fname):
+        f = aligner.extd2 if dual else aligner.extz2
+        r, cig = f(c["q"], c["t"], c["sc"], w=c["w"], zdrop=c["zdrop"], end_bonus=c["end_bonus"], flag=c["flag"])
+        assert same_result(c["res"], c["cigar"], r, cig), (c["name"], describe(c["res"], c["cigar"]), describe(r, cig))
+
+
+@pytest.mark.parametrize("preset,w,lens", [("asm5", 3001, (7000, 9000)), ("asm10", 3900, (8500, 9500)),
+                                            ("map-hifi", 751, (3000, 5000)), ("hifiasm", 500, (2500, 4000)),
+                                            ("map-ont", 2300, (5000, 6000))])
+def test_wide_band_classes(oracle, aligner, preset, w, lens):
+    """One task per DPX warps-per-task class (2, 4, 6, 8 warps) plus flags, against the oracle."""
+    rng = np.random.default_rng(31 + w)
+    pairs, flags = [], []
+    for i, L in enumerate(lens):
+        ref = synth.random_seq(rng, L)
+        q, _ = synth.plant_svs(rng, ref, 3, max_net=min(w // 2 - 50, 1000), max_len=min(w // 2 - 60, 800))
+        pairs.append((synth.mutate(rng, q, 0.004, 0.002, 0.002), ref))
+        flags.append([0, _abi.EZ_EXTZ_ONLY][i % 2])
+    from focalsv_b200.presets import PRESETS
+    g = synth._pack("wide." + preset, preset, pairs, w, PRESETS[preset].zdrop, flags=np.array(flags, dtype=np.int32))
+    before = aligner.stats()["exact_path_tasks"]
+    bad, ores, gres = compare_group(oracle, aligner, g)
+    assert not bad, (preset, bad)
+    assert aligner.stats()["exact_path_tasks"] == before
+
+
+def test_full_size_properties_cfg2_slice(oracle, aligner):
+    """BASELINE-size tasks (too big for the oracle's full check inside the test budget): size-independent
+    properties.  CIGAR consumes both sequences and re-scores to ez.score; score-only == with-CIGAR; re-running is
+    idempotent; cells equal the band definition when the task is not dropped."""
+    g = synth.config2(n_regions=12, seed=5, max_region=120000)[0]
+    res, cig = aligner.align_batch(g.scoring, g.qarena, g.tarena, g.tasks)
+    res2, cig2 = aligner.align_batch(g.scoring, g.qarena, g.tarena, g.tasks)
+    so = g.tasks.copy()
+    so["flag"] |= _abi.EZ_SCORE_ONLY
+    res3, _ = aligner.align_batch(g.scoring, g.qarena, g.tarena, so)
+    for f in _abi.EZ_FIELDS:
+        assert np.array_equal(res[f], res2[f])
+        if f != "n_cigar":
+            assert np.array_equal(res[f], res3[f]), f
+    assert np.array_equal(cig, cig2)
+    from focalsv_b200 import api
+    n_ok = 0
+    for i, t in enumerate(g.tasks):
+        q = g.qarena[t["q_off"]:t["q_off"] + t["qlen"]]
+        tt = g.tarena[t["t_off"]:t["t_off"] + t["tlen"]]
+        if int(res[i]["zdropped"]):
+            continue
+        n_ok += 1
+        c = task_cigar(res[i], cig)
+        s, qu, tu = oracle.score_cigar(q, tt, g.scoring, c)
+        assert (qu, tu) == (int(t["qlen"]), int(t["tlen"]))
+        assert s == int(res[i]["score"]), (i, s, int(res[i]["score"]))
+        assert int(res[i]["cells"]) == api.task_cells(int(t["qlen"]), int(t["tlen"]), int(t["w"]))
+    assert n_ok >= len(g.tasks) // 2
