@@ -5,32 +5,20 @@
 // a five-state walk {H, E, F, E~, F~} from the end cell towards (0,0), forced
 // states outside the stored band, leading D / I, optional reversal.
 //
-// B200 shape: one warp per task.  The walk is a pointer chase through HBM, so
-// instead of one dependent load per step the 32 lanes speculatively fetch the
-// next 32 cells along the direction the current state moves in (diagonal for H,
-// column for E/E~, row for F/F~), every lane evaluates the state machine for
-// "its" cell assuming the run continues, and one ballot finds where the run
-// really ends.  A run of n equal steps costs one memory round trip.
-// off[r] / off_end[r] of the reference are recomputed from r (band_limits), so
-// no per-row arrays are stored.
+// B200 shape: the walk runs in the fill kernel's own CTA right after the last
+// antidiagonal (the rows it reads first are the ones written last, still in L2), on
+// ONE warp.  It is a pointer chase, so instead of one dependent load per step the
+// 32 lanes speculatively fetch the next 32 cells along the direction the current
+// state moves in (diagonal for H, column for E/E~, row for F/F~), every lane
+// evaluates the state machine for "its" cell assuming the run continues, and one
+// ballot finds where the run really ends: a run of n equal steps costs one memory
+// round trip.  off[r] / off_end[r] of the reference are recomputed from r
+// (band_limits), so no per-row arrays are stored.  Two passes: count, then write into
+// an exactly-sized slice of the compact CIGAR arena (one atomicAdd per task).
 #pragma once
 #include "fsv_common.cuh"
 
 namespace fsv {
-
-constexpr int BT_THREADS = 128;   // 4 tasks per CTA
-
-struct BtParams {
-    const DevTask* tasks;
-    const int32_t* order;
-    int32_t n_order;
-    fsv_result* results;
-    DevAux* aux;
-    const uint8_t* tb;
-    uint32_t* cigar;          // compact CIGAR arena (write pass)
-    int64_t cigar_cap;        // words
-    int32_t* overflow;        // set when a CIGAR does not fit
-};
 
 // next state at a cell reached in state `s` (ksw2.h:133-136)
 __device__ __forceinline__ int bt_next_state(int s, int cell, int force)
@@ -42,32 +30,20 @@ __device__ __forceinline__ int bt_next_state(int s, int cell, int force)
     return ns;
 }
 
+// All 32 lanes of one warp call this.  Returns the number of CIGAR words; with WRITE it also stores
+// them (BAM encoding, len << 4 | op) at out[0 .. total).
 template <bool WRITE>
-__global__ void __launch_bounds__(BT_THREADS) fsv_backtrack_kernel(const BtParams P)
+__device__ int bt_walk(const TbPool& pool, const int32_t* table, const DevTask& T, int i0, int j0, uint32_t* out, int total)
 {
-    const int wslot = (blockIdx.x * BT_THREADS + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (wslot >= P.n_order) return;
-    const int ti = P.order[wslot];
-    const DevTask T = P.tasks[ti];
-    const DevAux A = P.aux[ti];
-    if (T.kind == 0 || A.i0 < 0 || A.j0 < 0 || T.tb_off < 0) {
-        if (!WRITE && lane == 0) { P.aux[ti].n_cigar = 0; P.results[T.orig].n_cigar = 0; }
-        return;
-    }
-    const uint8_t* tb = P.tb + T.tb_off;
     const bool keep_rev = (T.flag & FSV_EZ_REV_CIGAR) != 0;
-    const int total = A.n_cigar;                        // valid in the write pass
-    const int64_t out_base = WRITE ? P.results[T.orig].cigar_off : 0;
-    const bool fits = WRITE ? (out_base + total <= P.cigar_cap) : false;
-
-    int i = A.i0, j = A.j0, state = 0;
+    int i = i0, j = j0, state = 0;
     int cur_op = -1, cur_len = 0, n_out = 0;
     auto flush = [&]() {
         if (cur_len > 0) {
-            if (WRITE && fits && lane == 0) {
-                int pos = keep_rev ? n_out : total - 1 - n_out;
-                P.cigar[out_base + pos] = (uint32_t)cur_len << 4 | (uint32_t)cur_op;
+            if (WRITE && lane == 0) {
+                const int pos = keep_rev ? n_out : total - 1 - n_out;
+                out[pos] = (uint32_t)cur_len << 4 | (uint32_t)cur_op;
             }
             ++n_out;
         }
@@ -80,30 +56,33 @@ __global__ void __launch_bounds__(BT_THREADS) fsv_backtrack_kernel(const BtParam
 
     while (i >= 0 && j >= 0) {
         // lane l looks at the cell l steps further along the direction of `state`
-        int di = (state == 0 || state == 1 || state == 3) ? 1 : 0;
-        int dj = (state == 0 || state == 2 || state == 4) ? 1 : 0;
-        int li = i - di * lane, lj = j - dj * lane;
-        bool valid = li >= 0 && lj >= 0;
+        const int di = (state == 0 || state == 1 || state == 3) ? 1 : 0;
+        const int dj = (state == 0 || state == 2 || state == 4) ? 1 : 0;
+        const int li = i - di * lane, lj = j - dj * lane;
+        const bool valid = li >= 0 && lj >= 0;
         int ns = -1;
         if (valid) {
             int r = li + lj, st0, en0;
             band_limits(r, T.qlen, T.tlen, T.w, st0, en0);
-            int st = round_st(st0), en = round_en(en0);
+            const int st = round_st(st0), en = round_en(en0);
             int force = -1;
             if (li < st) force = 2;
             if (li > en) force = 1;
-            int cell = force < 0 ? tb[(int64_t)r * T.pitch + (li - st)] : 0;
-            // the DPX kernel stores the winner's priority code (tb_mode - d) in bits 0-2
-            if (T.tb_mode && force < 0) cell = (cell & ~7) | (T.tb_mode - (cell & 7));
+            int cell = 0;
+            if (force < 0) {
+                cell = tb_row(pool, table, T.rows_per_page, T.pitch, r)[li - st];
+                // the DPX kernel stores the winner's priority code (tb_mode - d) in bits 0-2
+                if (T.tb_mode) cell = (cell & ~7) | (T.tb_mode - (cell & 7));
+            }
             ns = bt_next_state(state, cell, force);
         }
-        unsigned cont = __ballot_sync(0xffffffffu, valid && ns == state);
+        const unsigned cont = __ballot_sync(0xffffffffu, valid && ns == state);
         int n = __ffs(~cont) - 1;            // leading lanes that stay in `state`
         if (n < 0) n = 32;
         if (n > 0) { emit(op_of(state), n); i -= di * n; j -= dj * n; }
         if (n < 32) {
-            int ns_n = __shfl_sync(0xffffffffu, ns, n);
-            bool valid_n = __shfl_sync(0xffffffffu, (int)valid, n) != 0;
+            const int ns_n = __shfl_sync(0xffffffffu, ns, n);
+            const bool valid_n = __shfl_sync(0xffffffffu, (int)valid, n) != 0;
             if (!valid_n) break;             // walked off the matrix
             state = ns_n;
             emit(op_of(state), 1);
@@ -115,50 +94,47 @@ __global__ void __launch_bounds__(BT_THREADS) fsv_backtrack_kernel(const BtParam
     if (i >= 0) emit(2, i + 1);              // leading deletion (ksw2.h:145)
     if (j >= 0) emit(1, j + 1);              // leading insertion (ksw2.h:146)
     flush();
-    if (!WRITE) {
-        if (lane == 0) { P.aux[ti].n_cigar = n_out; P.results[T.orig].n_cigar = n_out; }
-    } else if (!fits && lane == 0) atomicExch(P.overflow, 1);
+    return n_out;
 }
 
-// exclusive scan of n_cigar over the tasks of one chunk, continuing from *running
-// (single CTA; a chunk holds at most a few thousand tasks)
-__global__ void fsv_cigar_offsets_kernel(const DevTask* tasks, const int32_t* order, int32_t n_order,
-                                         const DevAux* aux, fsv_result* results, int64_t* running)
+// End of a task, executed by warp 0 of the CTA after a CTA barrier: end-point choice
+// (ksw2_extz2_sse.c:292-301), CIGAR into the arena, result record.
+__device__ inline void finish_task(const RunCtx& C, const DevTask& T, const int32_t* table, const EzState& ez,
+                                   int64_t cells, bool with_tb)
 {
-    __shared__ int64_t sh_warp[32];
-    __shared__ int64_t sh_base;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) sh_base = *running;
-    __syncthreads();
-    for (int base = 0; base < n_order; base += (int)blockDim.x) {
-        int idx = base + tid;
-        int64_t v = 0; int ti = -1;
-        if (idx < n_order) { ti = order[idx]; v = aux[ti].n_cigar; }
-        int64_t incl = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int64_t n = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += n;
-        }
-        if (lane == 31) sh_warp[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            int64_t wv = lane < (int)(blockDim.x >> 5) ? sh_warp[lane] : 0, wi = wv;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int64_t n = __shfl_up_sync(0xffffffffu, wi, o);
-                if (lane >= o) wi += n;
-            }
-            sh_warp[lane] = wi - wv;     // exclusive prefix of the warp totals
-        }
-        __syncthreads();
-        int64_t excl = sh_base + sh_warp[warp] + incl - v;
-        if (ti >= 0) results[tasks[ti].orig].cigar_off = excl;
-        __syncthreads();
-        if (tid == (int)blockDim.x - 1) sh_base = excl + v;
-        __syncthreads();
+    const int lane = threadIdx.x & 31;
+    int i0 = -1, j0 = -1, reach_end = 0;
+    if (with_tb) {
+        if (!ez.zdropped && !(T.flag & FSV_EZ_EXTZ_ONLY)) { i0 = T.tlen - 1; j0 = T.qlen - 1; }
+        else if (!ez.zdropped && (T.flag & FSV_EZ_EXTZ_ONLY) && ez.mqe + T.end_bonus > ez.max) {
+            reach_end = 1; i0 = ez.mqe_t; j0 = T.qlen - 1;
+        } else if (ez.max_t >= 0 && ez.max_q >= 0) { i0 = ez.max_t; j0 = ez.max_q; }
     }
-    if (tid == 0) *running = sh_base;
+    int n_cigar = 0;
+    long long off = 0;
+    if (i0 >= 0 && j0 >= 0) {
+        n_cigar = bt_walk<false>(C.pool, table, T, i0, j0, nullptr, 0);
+        if (lane == 0) off = (long long)atomicAdd(C.cigar_cursor, (unsigned long long)n_cigar);
+        off = __shfl_sync(0xffffffffu, off, 0);
+        if (off + n_cigar <= C.cigar_cap) bt_walk<true>(C.pool, table, T, i0, j0, C.cigar + off, n_cigar);
+        else if (lane == 0) atomicExch(C.overflow, 1);
+    }
+    if (lane == 0) {
+        fsv_result R;
+        R.max = ez.max; R.zdropped = ez.zdropped; R.max_q = ez.max_q; R.max_t = ez.max_t;
+        R.mqe = ez.mqe; R.mqe_t = ez.mqe_t; R.mte = ez.mte; R.mte_q = ez.mte_q; R.score = ez.score;
+        R.reach_end = reach_end; R.n_cigar = n_cigar; R.status = 0; R.cigar_off = off; R.cells = cells;
+        C.results[T.orig] = R;
+    }
+}
+
+__device__ inline void finish_reset_task(const RunCtx& C, const DevTask& T)
+{   // ksw2's silent returns (ksw2_extz2_sse.c:57,82): a successful task with a reset result
+    fsv_result R;
+    R.max = 0; R.zdropped = 0; R.max_q = R.max_t = R.mqe_t = R.mte_q = -1;
+    R.mqe = R.mte = R.score = FSV_NEG_INF; R.reach_end = 0; R.n_cigar = 0;
+    R.status = T.pad_; R.cigar_off = 0; R.cells = 0;
+    C.results[T.orig] = R;
 }
 
 }  // namespace fsv

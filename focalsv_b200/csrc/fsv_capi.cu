@@ -28,20 +28,24 @@ struct fsv_ctx {
     int device = 0;
     int sm_count = 0;
     size_t smem_optin = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;            // copies, timing events
+    cudaStream_t kstream[12] = {};            // one per concurrently running fill-kernel variant
     std::string last_error;
     fsv_stats stats{};
     // options
-    int64_t tb_budget = 0;      // bytes of traceback kept resident per chunk (0 = auto)
+    int64_t tb_budget = 0;      // bytes of the traceback page pool (0 = auto: 70% of free memory, at most what the batch needs)
     int force_exact = 0;        // route every task to the general int8-exact kernel
     int exact_smem_lanes = 4096;
+    int64_t page_bytes = 32ll << 20;
     // scratch shared by the batches of this context (one batch runs at a time)
-    uint8_t* d_tb = nullptr; size_t tb_cap = 0;
+    uint8_t* d_pool = nullptr; size_t pool_cap = 0;
     uint8_t* d_ws = nullptr; size_t ws_cap = 0;
+    int32_t* d_tables = nullptr; size_t tables_cap = 0;
+    int32_t* d_free_stack = nullptr; size_t stack_cap = 0;
 };
 
-struct Chunk { int32_t begin, end; int64_t tb_bytes; };
-struct DpxLaunch { int chunk, nw, with_tb, begin, count; };   // a slice of order_dpx for one kernel variant
+// one fill-kernel launch: a slice of the work list, largest task first
+struct Launch { int kind /*0 general, 1 DPX*/, nw, with_tb, begin, count, grid; int64_t table_off; };
 
 // any base code outside A,C,G,T (0..3)?  8 bytes at a time.
 static bool has_wildcard(const uint8_t* p, size_t n)
@@ -60,22 +64,21 @@ struct fsv_batch {
     bool dual = false;
     size_t n = 0;
     std::vector<DevTask> tasks;       // caller order
-    std::vector<int32_t> order_exact; // per chunk: tasks for the general kernel
-    std::vector<int32_t> order_all;   // processing order (largest first), chunked
-    std::vector<int32_t> order_dpx;   // per chunk: tasks for the DPX kernel (same index space as order_all)
-    std::vector<Chunk> chunks;
-    std::vector<DpxLaunch> dpx_launches;
+    std::vector<int32_t> work;        // task indices grouped per launch, largest first inside a group
+    std::vector<Launch> launches;
     std::vector<uint8_t> is_dpx;      // per task
     int64_t cigar_cap_words = 0;
     int64_t ws_lanes = 0;
+    int64_t pool_pages = 0;           // pages of the traceback pool this batch wants
+    int32_t max_pages_per_task = 1;
+    int64_t tb_bytes_total = 0;       // traceback bytes a full run writes
     // device
     uint8_t *d_q = nullptr, *d_t = nullptr;
     DevTask* d_tasks = nullptr;
-    int32_t *d_order_all = nullptr, *d_order_exact = nullptr, *d_order_dpx = nullptr;
+    int32_t* d_work = nullptr;
     fsv_result* d_results = nullptr;
-    DevAux* d_aux = nullptr;
-    int32_t* d_counters = nullptr;    // [0] exact cursor, [1] dpx cursor, [2] overflow flag
-    int64_t* d_running = nullptr;
+    int32_t* d_ctrl = nullptr;        // [0] overflow flag, [1] pool lock, [2] pool n_free; [8..] queue states (8 B each)
+    unsigned long long* d_cursor = nullptr;
     uint32_t* d_cigar = nullptr;
     int state = 0;                    // 0 created, 1 run
 };
@@ -130,6 +133,8 @@ extern "C" int fsv_init(int device, fsv_ctx** out)
     c->sm_count = prop.multiProcessorCount;
     c->smem_optin = prop.sharedMemPerBlockOptin;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; cudaGetLastError(); return FSV_ERR_CUDA; }
+    for (auto& ks : c->kstream)
+        if (cudaStreamCreateWithFlags(&ks, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); ks = nullptr; }
     *out = c;
     return FSV_OK;
 }
@@ -138,8 +143,11 @@ extern "C" void fsv_destroy(fsv_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    if (c->d_tb) cudaFree(c->d_tb);
+    if (c->d_pool) cudaFree(c->d_pool);
     if (c->d_ws) cudaFree(c->d_ws);
+    if (c->d_tables) cudaFree(c->d_tables);
+    if (c->d_free_stack) cudaFree(c->d_free_stack);
+    for (auto ks : c->kstream) if (ks) cudaStreamDestroy(ks);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -156,6 +164,10 @@ extern "C" int fsv_set_option(fsv_ctx* c, const char* key, int64_t value)
     if (!c || !key) return FSV_ERR_INVALID;
     if (!strcmp(key, "traceback_budget_bytes")) { c->tb_budget = value; return FSV_OK; }
     if (!strcmp(key, "force_exact")) { c->force_exact = (int)value; return FSV_OK; }
+    if (!strcmp(key, "traceback_page_bytes")) {
+        if (value < (1 << 16) || (value & 255)) return FSV_ERR_INVALID;
+        c->page_bytes = value; return FSV_OK;
+    }
     if (!strcmp(key, "exact_smem_lanes")) {
         if (value < 256 || (value & (value - 1))) return FSV_ERR_INVALID;
         c->exact_smem_lanes = (int)value; return FSV_OK;
@@ -241,9 +253,8 @@ static int64_t pow2_at_least(int64_t x) { int64_t p = 1; while (p < x) p <<= 1; 
 
 static void free_batch_device(fsv_batch* b)
 {
-    cudaFree(b->d_q); cudaFree(b->d_t); cudaFree(b->d_tasks); cudaFree(b->d_order_all); cudaFree(b->d_order_exact);
-    cudaFree(b->d_order_dpx); cudaFree(b->d_results); cudaFree(b->d_aux); cudaFree(b->d_counters);
-    cudaFree(b->d_running); cudaFree(b->d_cigar);
+    cudaFree(b->d_q); cudaFree(b->d_t); cudaFree(b->d_tasks); cudaFree(b->d_work); cudaFree(b->d_results);
+    cudaFree(b->d_ctrl); cudaFree(b->d_cursor); cudaFree(b->d_cigar);
 }
 
 extern "C" void fsv_batch_destroy(fsv_batch* b)
@@ -252,6 +263,23 @@ extern "C" void fsv_batch_destroy(fsv_batch* b)
     cudaSetDevice(b->ctx->device);
     free_batch_device(b);
     delete b;
+}
+
+static int exact_grid(fsv_ctx* c, bool dual, int n_tasks)
+{
+    const size_t smem = (size_t)c->exact_smem_lanes * (EXACT_NARR + 4);
+    int per_sm = 0;
+    cudaError_t e;
+    if (dual) {
+        cudaFuncSetAttribute(fsv_fill_exact_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fsv_fill_exact_kernel<true>, EXACT_THREADS, smem);
+    } else {
+        cudaFuncSetAttribute(fsv_fill_exact_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fsv_fill_exact_kernel<false>, EXACT_THREADS, smem);
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); per_sm = 1; }
+    if (per_sm < 1) per_sm = 1;
+    return std::max(1, std::min(n_tasks, c->sm_count * per_sm));
 }
 
 extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
@@ -272,14 +300,14 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
     // ---- task table
     b->tasks.resize(n);
     b->is_dpx.assign(n, 0);
-    int64_t cigar_words = 0;
+    int64_t cigar_words = 0, pages_total = 0;
     for (size_t i = 0; i < n; ++i) {
         const fsv_task& t = tasks[i];
         DevTask& d = b->tasks[i];
         memset(&d, 0, sizeof d);
         d.q_off = t.q_off; d.t_off = t.t_off; d.qlen = t.qlen; d.tlen = t.tlen;
         d.zdrop = t.zdrop; d.end_bonus = t.end_bonus; d.flag = t.flag; d.orig = (int32_t)i; d.tb_off = -1;
-        d.kind = 1;
+        d.kind = 1; d.rows_per_page = 1;
         if (all_reset || t.qlen <= 0 || t.tlen <= 0) { d.kind = 0; d.pad_ = all_reset ? reset_status : 0; continue; }
         if (t.q_off < 0 || t.t_off < 0 || (uint64_t)t.q_off + (uint64_t)t.qlen > qbytes ||
             (uint64_t)t.t_off + (uint64_t)t.tlen > tbytes || (int64_t)t.qlen + t.tlen > 0x7ffffff0) {
@@ -292,7 +320,19 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
         int n_col = (std::min(mn, w + 1) + 15) / 16 + 1;                          // :75-76
         d.pitch = n_col * 16;
         d.cells_est = cells_estimate(t.qlen, t.tlen, w);
-        if (!(t.flag & FSV_EZ_SCORE_ONLY)) cigar_words += (int64_t)t.qlen + t.tlen + 2;
+        if (!(t.flag & FSV_EZ_SCORE_ONLY)) {
+            cigar_words += (int64_t)t.qlen + t.tlen + 2;
+            if (d.pitch > c->page_bytes) {
+                c->last_error = "task " + std::to_string(i) + ": one traceback row exceeds the page size";
+                delete b; return FSV_ERR_NOMEM;
+            }
+            d.rows_per_page = (int32_t)(c->page_bytes / d.pitch);
+            int64_t rows = (int64_t)t.qlen + t.tlen - 1;
+            d.tb_pages = (int32_t)((rows + d.rows_per_page - 1) / d.rows_per_page);
+            pages_total += d.tb_pages;
+            b->max_pages_per_task = std::max(b->max_pages_per_task, d.tb_pages);
+            b->tb_bytes_total += rows * d.pitch;
+        }
         if (!c->force_exact) {
             // the DPX kernel packs bases in 2 bits: a task with a wildcard base goes to the general kernel
             const bool wild = has_wildcard(qarena + t.q_off, (size_t)t.qlen) || has_wildcard(tarena + t.t_off, (size_t)t.tlen);
@@ -305,67 +345,53 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
     }
     b->cigar_cap_words = cigar_words;
 
-    // ---- processing order: largest first (LPT within the device), cut into chunks
-    // whose traceback rows fit the resident budget
+    // ---- traceback page pool: what the batch needs, capped by the budget
+    {
+        int64_t budget = c->tb_budget;
+        if (budget <= 0) {
+            size_t fr = 0, tot = 0;
+            CK(c, cudaMemGetInfo(&fr, &tot));
+            fr += c->pool_cap;                       // the pool of a previous batch is reused
+            budget = (int64_t)(fr * 0.70);
+        }
+        int64_t cap_pages = std::max<int64_t>(budget / c->page_bytes, 0);
+        b->pool_pages = std::min(pages_total, cap_pages);
+        if (b->max_pages_per_task > 1 || pages_total > 0)
+            if (b->pool_pages < b->max_pages_per_task) {
+                c->last_error = "the traceback of the largest task (" + std::to_string(b->max_pages_per_task) +
+                                " pages) does not fit the pool (" + std::to_string(cap_pages) + " pages)";
+                delete b; return FSV_ERR_NOMEM;
+            }
+    }
+
+    // ---- work lists: one per kernel variant (general; DPX by warps-per-task class and with/without
+    // traceback), each sorted largest-first (LPT within the device)
     std::vector<int32_t> ord(n);
     for (size_t i = 0; i < n; ++i) ord[i] = (int32_t)i;
     std::stable_sort(ord.begin(), ord.end(), [&](int32_t a, int32_t x) { return b->tasks[a].cells_est > b->tasks[x].cells_est; });
-    int64_t budget = c->tb_budget;
-    if (budget <= 0) {
-        size_t fr = 0, tot = 0;
-        CK(c, cudaMemGetInfo(&fr, &tot));
-        budget = (int64_t)(fr * 0.70);
-    }
-    b->order_all = ord;
-    {
-        Chunk ch{0, 0, 0};
+    int64_t ws_need = 0, table_off = 0;
+    auto add_launch = [&](int kind, int nw, int with_tb) {
+        Launch L{kind, nw, with_tb, (int)b->work.size(), 0, 0, 0};
         for (size_t k = 0; k < n; ++k) {
-            DevTask& d = b->tasks[ord[k]];
-            int64_t need = 0;
-            if (d.kind == 1 && !(d.flag & FSV_EZ_SCORE_ONLY))
-                need = ((int64_t)(d.qlen + d.tlen - 1) * d.pitch + 255) / 256 * 256;
-            if (need > budget) {
-                c->last_error = "traceback of task " + std::to_string(d.orig) + " (" + std::to_string(need) +
-                                " bytes) exceeds the resident budget";
-                delete b; return FSV_ERR_NOMEM;
-            }
-            if (ch.tb_bytes + need > budget && (int32_t)k > ch.begin) {
-                ch.end = (int32_t)k; b->chunks.push_back(ch);
-                ch = Chunk{(int32_t)k, 0, 0};
-            }
-            if (need) { d.tb_off = ch.tb_bytes; ch.tb_bytes += need; }
+            const int ti = ord[k];
+            const DevTask& d = b->tasks[ti];
+            if (kind == 0) { if (b->is_dpx[ti]) continue; }
+            else if (!b->is_dpx[ti] || d.nw != nw || (int)!(d.flag & FSV_EZ_SCORE_ONLY) != with_tb) continue;
+            b->work.push_back(ti);
+            if (kind == 0 && d.kind == 1 && d.pitch + 96 > c->exact_smem_lanes) ws_need = std::max<int64_t>(ws_need, d.pitch + 96);
         }
-        ch.end = (int32_t)n;
-        if (ch.end > ch.begin) b->chunks.push_back(ch);
-    }
-    // per chunk, split the order into work lists: one per kernel variant (general; DPX by
-    // warps-per-task class and with/without traceback), each still largest-first
-    b->order_exact.assign(n, -1); b->order_dpx.assign(n, -1);
-    int64_t ws_need = 0;
-    for (size_t ci = 0; ci < b->chunks.size(); ++ci) {
-        auto& ch = b->chunks[ci];
-        int ne = 0, nd = 0;
-        for (int k = ch.begin; k < ch.end; ++k) {
-            int ti = ord[k];
-            if (b->is_dpx[ti]) continue;
-            b->order_exact[ch.begin + ne++] = ti;
-            if (b->tasks[ti].kind == 1 && b->tasks[ti].pitch + 96 > c->exact_smem_lanes)
-                ws_need = std::max<int64_t>(ws_need, b->tasks[ti].pitch + 96);
-        }
-        static const int kClasses[5] = {8, 6, 4, 2, 1};
-        for (int cls : kClasses)
-            for (int with_tb = 1; with_tb >= 0; --with_tb) {
-                int begin = ch.begin + nd;
-                for (int k = ch.begin; k < ch.end; ++k) {
-                    int ti = ord[k];
-                    if (!b->is_dpx[ti] || b->tasks[ti].nw != cls) continue;
-                    if ((int)!(b->tasks[ti].flag & FSV_EZ_SCORE_ONLY) != with_tb) continue;
-                    b->order_dpx[ch.begin + nd++] = ti;
-                }
-                if (ch.begin + nd > begin) b->dpx_launches.push_back(DpxLaunch{(int)ci, cls, with_tb, begin, ch.begin + nd - begin});
-            }
-    }
+        L.count = (int)b->work.size() - L.begin;
+        if (!L.count) return;
+        L.grid = kind == 0 ? exact_grid(c, b->dual, L.count) : dpx_grid(c->sm_count, b->dual, with_tb != 0, nw, L.count);
+        L.table_off = table_off;
+        table_off += (int64_t)L.grid * b->max_pages_per_task;
+        b->launches.push_back(L);
+    };
+    static const int kClasses[5] = {8, 6, 4, 2, 1};
+    for (int cls : kClasses) for (int with_tb = 1; with_tb >= 0; --with_tb) add_launch(1, cls, with_tb);
+    add_launch(0, 0, 0);
     b->ws_lanes = ws_need ? pow2_at_least(ws_need) : 0;
+    if (b->launches.size() > 12) { delete b; return FSV_ERR_INVALID; }
 
     // ---- device buffers + H2D
     auto fail = [&](int code) { free_batch_device(b); delete b; return code; };
@@ -381,66 +407,31 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
     CKB(cudaMalloc(&b->d_q, qbytes + 64));
     CKB(cudaMalloc(&b->d_t, tbytes + 64));
     CKB(cudaMalloc(&b->d_tasks, (n + 1) * sizeof(DevTask)));
-    CKB(cudaMalloc(&b->d_order_all, (n + 1) * 4));
-    CKB(cudaMalloc(&b->d_order_exact, (n + 1) * 4));
-    CKB(cudaMalloc(&b->d_order_dpx, (n + 1) * 4));
+    CKB(cudaMalloc(&b->d_work, (n + 1) * 4));
     CKB(cudaMalloc(&b->d_results, (n + 1) * sizeof(fsv_result)));
-    CKB(cudaMalloc(&b->d_aux, (n + 1) * sizeof(DevAux)));
-    CKB(cudaMalloc(&b->d_counters, 64));
-    CKB(cudaMalloc(&b->d_running, 64));
+    CKB(cudaMalloc(&b->d_ctrl, 256));
+    CKB(cudaMalloc(&b->d_cursor, 64));
     CKB(cudaMalloc(&b->d_cigar, (size_t)(b->cigar_cap_words + 4) * 4));
     if (qbytes) CKB(cudaMemcpyAsync(b->d_q, qarena, qbytes, cudaMemcpyHostToDevice, c->stream));
     if (tbytes) CKB(cudaMemcpyAsync(b->d_t, tarena, tbytes, cudaMemcpyHostToDevice, c->stream));
     if (n) {
         CKB(cudaMemcpyAsync(b->d_tasks, b->tasks.data(), n * sizeof(DevTask), cudaMemcpyHostToDevice, c->stream));
-        CKB(cudaMemcpyAsync(b->d_order_all, b->order_all.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
-        CKB(cudaMemcpyAsync(b->d_order_exact, b->order_exact.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
-        CKB(cudaMemcpyAsync(b->d_order_dpx, b->order_dpx.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
+        CKB(cudaMemcpyAsync(b->d_work, b->work.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
     }
     CKB(cudaStreamSynchronize(c->stream));
 #undef CKB
-    c->stats.h2d_bytes += (int64_t)(qbytes + tbytes + n * (sizeof(DevTask) + 12));
+    c->stats.h2d_bytes += (int64_t)(qbytes + tbytes + n * (sizeof(DevTask) + 4));
     *out = b;
     return FSV_OK;
 }
 
-static int ensure_scratch(fsv_ctx* c, size_t tb_bytes, size_t ws_bytes)
+template <typename T>
+static int grow(fsv_ctx* c, T** p, size_t* cap, size_t bytes)
 {
-    if (tb_bytes > c->tb_cap) {
-        if (c->d_tb) { cudaFree(c->d_tb); c->d_tb = nullptr; c->tb_cap = 0; }
-        CK(c, cudaMalloc(&c->d_tb, tb_bytes + 256));
-        c->tb_cap = tb_bytes;
-    }
-    if (ws_bytes > c->ws_cap) {
-        if (c->d_ws) { cudaFree(c->d_ws); c->d_ws = nullptr; c->ws_cap = 0; }
-        CK(c, cudaMalloc(&c->d_ws, ws_bytes + 256));
-        c->ws_cap = ws_bytes;
-    }
-    return FSV_OK;
-}
-
-template <bool DUAL>
-static int launch_exact(fsv_ctx* c, fsv_batch* b, const Chunk& ch, int n_exact)
-{
-    if (n_exact <= 0) return FSV_OK;
-    const size_t smem = (size_t)c->exact_smem_lanes * (EXACT_NARR + 4);
-    auto kern = fsv_fill_exact_kernel<DUAL>;
-    CK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EXACT_THREADS, smem));
-    if (per_sm < 1) per_sm = 1;
-    int grid = std::min(n_exact, c->sm_count * per_sm);
-    size_t ws_bytes = b->ws_lanes ? (size_t)grid * (size_t)b->ws_lanes * (EXACT_NARR + 4) : 0;
-    int rc = ensure_scratch(c, 0, ws_bytes);
-    if (rc != FSV_OK) return rc;
-    FillParams P{};
-    P.qarena = b->d_q; P.tarena = b->d_t; P.tasks = b->d_tasks;
-    P.order = b->d_order_exact + ch.begin; P.n_order = n_exact; P.counter = b->d_counters + 0;
-    P.results = b->d_results; P.aux = b->d_aux; P.tb = c->d_tb; P.ws = c->d_ws; P.ws_lanes = b->ws_lanes;
-    P.smem_lanes = c->exact_smem_lanes; P.sc = b->sc;
-    kern<<<grid, EXACT_THREADS, smem, c->stream>>>(P);
-    CK(c, cudaGetLastError());
-    c->stats.fill_launches++;
+    if (bytes <= *cap) return FSV_OK;
+    if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
+    CK(c, cudaMalloc(p, bytes + 256));
+    *cap = bytes;
     return FSV_OK;
 }
 
@@ -449,70 +440,75 @@ extern "C" int fsv_batch_run(fsv_batch* b)
     if (!b) return FSV_ERR_INVALID;
     fsv_ctx* c = b->ctx;
     CK(c, cudaSetDevice(c->device));
+    // ---- scratch: page pool, free stack, page tables, general-kernel windows
+    int64_t tables = 0, ws_bytes = 0;
+    for (auto& L : b->launches) {
+        tables = std::max<int64_t>(tables, L.table_off + (int64_t)L.grid * b->max_pages_per_task);
+        if (L.kind == 0 && b->ws_lanes) ws_bytes = (int64_t)L.grid * b->ws_lanes * (EXACT_NARR + 4);
+    }
+    int rc;
+    if ((rc = grow(c, &c->d_pool, &c->pool_cap, (size_t)(b->pool_pages * c->page_bytes))) != FSV_OK) return rc;
+    if ((rc = grow(c, &c->d_free_stack, &c->stack_cap, (size_t)(b->pool_pages + 1) * 4)) != FSV_OK) return rc;
+    if ((rc = grow(c, &c->d_tables, &c->tables_cap, (size_t)(tables + 1) * 4)) != FSV_OK) return rc;
+    if ((rc = grow(c, &c->d_ws, &c->ws_cap, (size_t)ws_bytes)) != FSV_OK) return rc;
+    {   // control block: overflow flag, pool lock, free count, queue states; free stack = every page
+        std::vector<int32_t> stack((size_t)b->pool_pages + 1);
+        for (int64_t i = 0; i < b->pool_pages; ++i) stack[(size_t)i] = (int32_t)i;
+        CK(c, cudaMemcpyAsync(c->d_free_stack, stack.data(), (size_t)(b->pool_pages + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+        int32_t ctrl[64] = {0};
+        ctrl[2] = (int32_t)b->pool_pages;
+        for (size_t i = 0; i < b->launches.size(); ++i) {
+            unsigned long long st = (unsigned long long)(unsigned)b->launches[i].count;    // head 0, tail count
+            memcpy(&ctrl[8 + 2 * i], &st, 8);
+        }
+        CK(c, cudaMemcpyAsync(b->d_ctrl, ctrl, sizeof ctrl, cudaMemcpyHostToDevice, c->stream));
+        CK(c, cudaMemsetAsync(b->d_cursor, 0, 64, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));      // `stack` and `ctrl` are stack/heap temporaries
+    }
+    RunCtx R{};
+    R.qarena = b->d_q; R.tarena = b->d_t; R.tasks = b->d_tasks; R.results = b->d_results;
+    R.pool.base = c->d_pool; R.pool.page_bytes = c->page_bytes; R.pool.n_pages = (int32_t)b->pool_pages;
+    R.pool.free_stack = c->d_free_stack; R.pool.n_free = b->d_ctrl + 2; R.pool.lock = b->d_ctrl + 1;
+    R.max_pages_per_task = b->max_pages_per_task;
+    R.cigar = b->d_cigar; R.cigar_cursor = b->d_cursor; R.cigar_cap = b->cigar_cap_words; R.overflow = b->d_ctrl + 0;
+    R.sc = b->sc;
+
     cudaEvent_t e0, e1;
     CK(c, cudaEventCreate(&e0)); CK(c, cudaEventCreate(&e1));
-    std::vector<cudaEvent_t> evs;   // per chunk: fill begin, fill end, backtrack end
-    size_t tb_max = 0;
-    for (auto& ch : b->chunks) tb_max = std::max<size_t>(tb_max, (size_t)ch.tb_bytes);
-    int rc = ensure_scratch(c, tb_max, 0);
-    if (rc != FSV_OK) return rc;
-    CK(c, cudaMemsetAsync(b->d_running, 0, 64, c->stream));
-    CK(c, cudaMemsetAsync(b->d_counters, 0, 64, c->stream));
+    std::vector<cudaEvent_t> done(b->launches.size());
     CK(c, cudaEventRecord(e0, c->stream));
-    int64_t tb_total = 0;
-    for (size_t ci = 0; ci < b->chunks.size(); ++ci) {
-        auto& ch = b->chunks[ci];
-        int n_exact = 0;
-        for (int k = ch.begin; k < ch.end; ++k) if (b->order_exact[k] >= 0) ++n_exact;
-        cudaEvent_t a, m, z;
-        CK(c, cudaEventCreate(&a)); CK(c, cudaEventCreate(&m)); CK(c, cudaEventCreate(&z));
-        evs.push_back(a); evs.push_back(m); evs.push_back(z);
-        CK(c, cudaMemsetAsync(b->d_counters, 0, 8, c->stream));          // [0] general-kernel cursor
-        CK(c, cudaMemsetAsync(b->d_counters + 4, 0, 48, c->stream));     // [4..15] one cursor per DPX launch
-        CK(c, cudaEventRecord(a, c->stream));
-        int slot = 4;
-        for (const DpxLaunch& L : b->dpx_launches) {
-            if (L.chunk != (int)ci) continue;
-            DpxParams D{};
-            D.qarena = b->d_q; D.tarena = b->d_t; D.tasks = b->d_tasks; D.order = b->d_order_dpx + L.begin;
-            D.n_order = L.count; D.counter = b->d_counters + slot++; D.results = b->d_results; D.aux = b->d_aux;
-            D.tb = c->d_tb; D.sc = b->sc;
-            rc = dpx_launch(c->stream, c->sm_count, b->dual, L.with_tb != 0, L.nw, D, &c->last_error);
+    // every kernel variant runs concurrently on its own stream; they share the page pool, so the long
+    // tasks of one class overlap the short tasks of all the others
+    for (size_t i = 0; i < b->launches.size(); ++i) {
+        const Launch& L = b->launches[i];
+        cudaStream_t ks = c->kstream[i] ? c->kstream[i] : c->stream;
+        CK(c, cudaStreamWaitEvent(ks, e0, 0));
+        TaskQueue Q{reinterpret_cast<unsigned long long*>(b->d_ctrl + 8 + 2 * i), b->d_work + L.begin};
+        R.page_tables = c->d_tables + L.table_off;
+        if (L.kind == 1) {
+            DpxParams D{R, Q};
+            rc = dpx_launch(ks, b->dual, L.with_tb != 0, L.nw, L.grid, D, &c->last_error);
             if (rc != FSV_OK) return rc;
-            c->stats.fill_launches++;
+        } else {
+            FillParams P{R, Q, c->d_ws, b->ws_lanes, c->exact_smem_lanes};
+            const size_t smem = (size_t)c->exact_smem_lanes * (EXACT_NARR + 4);
+            if (b->dual) fsv_fill_exact_kernel<true><<<L.grid, EXACT_THREADS, smem, ks>>>(P);
+            else fsv_fill_exact_kernel<false><<<L.grid, EXACT_THREADS, smem, ks>>>(P);
+            CK(c, cudaGetLastError());
         }
-        rc = b->dual ? launch_exact<true>(c, b, ch, n_exact) : launch_exact<false>(c, b, ch, n_exact);
-        if (rc != FSV_OK) return rc;
-        CK(c, cudaEventRecord(m, c->stream));
-        // CIGAR reconstruction: count -> offsets -> write
-        int n_all = ch.end - ch.begin;
-        BtParams Q{};
-        Q.tasks = b->d_tasks; Q.order = b->d_order_all + ch.begin; Q.n_order = n_all; Q.results = b->d_results;
-        Q.aux = b->d_aux; Q.tb = c->d_tb; Q.cigar = b->d_cigar; Q.cigar_cap = b->cigar_cap_words;
-        Q.overflow = b->d_counters + 2;
-        int bt_grid = (n_all * 32 + BT_THREADS - 1) / BT_THREADS;
-        fsv_backtrack_kernel<false><<<bt_grid, BT_THREADS, 0, c->stream>>>(Q);
-        fsv_cigar_offsets_kernel<<<1, 1024, 0, c->stream>>>(b->d_tasks, b->d_order_all + ch.begin, n_all, b->d_aux,
-                                                            b->d_results, b->d_running);
-        fsv_backtrack_kernel<true><<<bt_grid, BT_THREADS, 0, c->stream>>>(Q);
-        CK(c, cudaGetLastError());
-        c->stats.backtrack_launches += 2; c->stats.other_launches += 1;
-        CK(c, cudaEventRecord(z, c->stream));
-        tb_total += ch.tb_bytes;
+        c->stats.fill_launches++;
+        CK(c, cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+        CK(c, cudaEventRecord(done[i], ks));
+        CK(c, cudaStreamWaitEvent(c->stream, done[i], 0));
     }
     CK(c, cudaEventRecord(e1, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     float ms = 0;
     CK(c, cudaEventElapsedTime(&ms, e0, e1));
-    c->stats.total_ms = ms; c->stats.fill_ms = 0; c->stats.backtrack_ms = 0;
-    for (size_t i = 0; i + 2 < evs.size() + 0; i += 3) {
-        float f = 0, g = 0;
-        cudaEventElapsedTime(&f, evs[i], evs[i + 1]); cudaEventElapsedTime(&g, evs[i + 1], evs[i + 2]);
-        c->stats.fill_ms += f; c->stats.backtrack_ms += g;
-    }
-    for (auto e : evs) cudaEventDestroy(e);
+    for (auto e : done) cudaEventDestroy(e);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    c->stats.traceback_bytes = tb_total;
+    c->stats.total_ms = ms; c->stats.fill_ms = ms; c->stats.backtrack_ms = 0;   // the CIGAR walk runs inside the fill kernels
+    c->stats.traceback_bytes = b->tb_bytes_total;
     c->stats.tasks += (int64_t)b->n;
     int64_t ne = 0;
     for (size_t i = 0; i < b->n; ++i) if (!b->is_dpx[i]) ++ne;
@@ -529,7 +525,7 @@ extern "C" int fsv_batch_fetch(fsv_batch* b, fsv_result* out, uint32_t* cigar, s
     CK(c, cudaSetDevice(c->device));
     int64_t used = 0;
     if (b->n) CK(c, cudaMemcpyAsync(out, b->d_results, b->n * sizeof(fsv_result), cudaMemcpyDeviceToHost, c->stream));
-    CK(c, cudaMemcpyAsync(&used, b->d_running, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(&used, b->d_cursor, 8, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     if (cigar_used) *cigar_used = (size_t)used;
     int64_t cells = 0;

@@ -28,6 +28,8 @@ struct DevTask {
     int32_t pad_;           // kind 0: the status to report
     int32_t tb_mode;        // traceback direction encoding: 0 = ksw2's d, n > 0 = (n - d) (DPX kernel)
     int32_t nw;             // DPX kernel: warps per task (0 = general kernel)
+    int32_t tb_pages;       // traceback pages this task needs (0 = score only)
+    int32_t rows_per_page;  // antidiagonals per page
 };
 
 // where the CIGAR walk of a task starts (ksw2_extz2_sse.c:292-301)
@@ -83,5 +85,128 @@ struct EzState {
         return 0;
     }
 };
+
+}  // namespace fsv
+
+namespace fsv {
+
+// ---------------------------------------------------------------------------
+// Paged traceback pool.  Traceback rows (one per antidiagonal, `pitch` bytes) of a task live in
+// fixed-size pages taken from one device-wide pool when the task STARTS and given back when its
+// CIGAR has been reconstructed, so the resident traceback is bounded by the tasks in flight
+// (one per CTA), not by the batch.  Row r of a task sits in page r / rows_per_page.
+struct TbPool {
+    uint8_t* base;          // n_pages * page_bytes
+    int64_t page_bytes;
+    int32_t n_pages;
+    int32_t* free_stack;    // page ids, free_stack[0 .. *n_free)
+    int32_t* n_free;
+    int32_t* lock;          // 0 = free
+};
+
+__device__ __forceinline__ void pool_lock(int32_t* lock)
+{
+    unsigned ns = 64;
+    while (atomicCAS(lock, 0, 1) != 0) { __nanosleep(ns); if (ns < 4096) ns <<= 1; }
+    __threadfence();
+}
+__device__ __forceinline__ void pool_unlock(int32_t* lock)
+{
+    __threadfence();
+    atomicExch(lock, 0);
+}
+// called by ONE thread; returns false when fewer than n pages are free
+__device__ inline bool pool_try_alloc(const TbPool& P, int n, int32_t* table)
+{
+    if (n <= 0) return true;
+    bool ok = false;
+    pool_lock(P.lock);
+    int nf = *(volatile int32_t*)P.n_free;
+    if (nf >= n) {
+        for (int i = 0; i < n; ++i) table[i] = ((volatile int32_t*)P.free_stack)[nf - 1 - i];
+        *(volatile int32_t*)P.n_free = nf - n;
+        ok = true;
+    }
+    pool_unlock(P.lock);
+    return ok;
+}
+__device__ inline void pool_free(const TbPool& P, int n, const int32_t* table)
+{
+    if (n <= 0) return;
+    pool_lock(P.lock);
+    int nf = *(volatile int32_t*)P.n_free;
+    for (int i = 0; i < n; ++i) ((volatile int32_t*)P.free_stack)[nf + i] = table[i];
+    *(volatile int32_t*)P.n_free = nf + n;
+    pool_unlock(P.lock);
+}
+
+// ---------------------------------------------------------------------------
+// Two-ended work queue over a task list sorted largest-first: CTAs take from the head; a CTA whose
+// head task does not get its traceback pages yet keeps it pending and works on tasks from the TAIL
+// (the smallest ones) meanwhile, so the few very long tasks never leave the device idle.
+struct TaskQueue {
+    unsigned long long* state;   // (head << 32) | tail over order[0..n)
+    const int32_t* order;
+};
+// end: 0 = head, 1 = tail.  Returns the task index or -1 when the queue is empty.
+__device__ inline int queue_take(const TaskQueue& Q, int end)
+{
+    unsigned long long s = *(volatile unsigned long long*)Q.state;
+    for (;;) {
+        unsigned head = (unsigned)(s >> 32), tail = (unsigned)(s & 0xffffffffu);
+        if (head >= tail) return -1;
+        unsigned long long ns = end == 0 ? (((unsigned long long)(head + 1) << 32) | tail)
+                                         : (((unsigned long long)head << 32) | (tail - 1));
+        unsigned long long old = atomicCAS(Q.state, s, ns);
+        if (old == s) return Q.order[end == 0 ? head : tail - 1];
+        s = old;
+    }
+}
+
+// everything a fill kernel needs besides its own parameters
+struct RunCtx {
+    const uint8_t* qarena;
+    const uint8_t* tarena;
+    const DevTask* tasks;
+    fsv_result* results;
+    TbPool pool;
+    int32_t* page_tables;        // per CTA: max_pages_per_task entries
+    int32_t max_pages_per_task;
+    uint32_t* cigar;             // compact CIGAR arena
+    unsigned long long* cigar_cursor;
+    int64_t cigar_cap;           // words
+    int32_t* overflow;           // set when the arena is too small
+    DevScoring sc;
+};
+
+// Picks the next task for this CTA (thread 0 only) and gets its traceback pages.
+// `pending` carries a claimed task that is still waiting for memory.  Returns the task index or -1.
+__device__ inline int next_task(const RunCtx& C, const TaskQueue& Q, int32_t* table, int& pending)
+{
+    for (;;) {
+        if (pending >= 0) {
+            if (pool_try_alloc(C.pool, C.tasks[pending].tb_pages, table)) { int t = pending; pending = -1; return t; }
+            int t = queue_take(Q, 1);                       // memory is short: do a small task meanwhile
+            if (t >= 0) {
+                if (pool_try_alloc(C.pool, C.tasks[t].tb_pages, table)) return t;
+                // not even the small one fits right now: wait for running tasks to finish
+                for (;;) { __nanosleep(2000); if (pool_try_alloc(C.pool, C.tasks[t].tb_pages, table)) return t; }
+            }
+            __nanosleep(2000);                              // queue drained: wait for memory
+            continue;
+        }
+        int t = queue_take(Q, 0);
+        if (t < 0) return -1;
+        if (pool_try_alloc(C.pool, C.tasks[t].tb_pages, table)) return t;
+        pending = t;
+    }
+}
+
+// byte address of traceback row r of a task (rows_per_page = page_bytes / pitch)
+__device__ __forceinline__ uint8_t* tb_row(const TbPool& P, const int32_t* table, int rows_per_page, int pitch, int r)
+{
+    const int pg = r / rows_per_page;
+    return P.base + (int64_t)table[pg] * P.page_bytes + (int64_t)(r - pg * rows_per_page) * pitch;
+}
 
 }  // namespace fsv

@@ -23,6 +23,7 @@
 #pragma once
 #include <string>
 
+#include "fsv_backtrack.cuh"
 #include "fsv_common.cuh"
 
 namespace fsv {
@@ -30,16 +31,8 @@ namespace fsv {
 constexpr int DPX_MAX_WARPS = 8;
 
 struct DpxParams {
-    const uint8_t* qarena;
-    const uint8_t* tarena;
-    const DevTask* tasks;
-    const int32_t* order;
-    int32_t n_order;
-    int32_t* counter;
-    fsv_result* results;
-    DevAux* aux;
-    uint8_t* tb;
-    DevScoring sc;
+    RunCtx C;
+    TaskQueue Q;
 };
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
@@ -186,7 +179,7 @@ template <bool DUAL, bool TB, int NW>
 __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kernel(const DpxParams P)
 {
     constexpr int NT = NW * 32;
-    using C = DpxConst<DUAL>;
+    using KC = DpxConst<DUAL>;
     __shared__ int32_t sh_task;
     __shared__ uint32_t sh_bx[2][NW], sh_bv[2][NW], sh_bx2[2][NW], sh_bq[2][NW];   // lane 15 of each warp's last vector
     __shared__ int32_t sh_bh[2][NW];                                   // ... and its H
@@ -194,24 +187,28 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
     __shared__ uint32_t sh_key[3];                                     // best tie key of an antidiagonal
     __shared__ int32_t sh_hen0[3], sh_hst0[3];                         // H[en0], H[st0]
     __shared__ int32_t sh_stop;                                        // iteration at which warp 0 saw the z-drop
-    const DevScoring& sc = P.sc;
+    const RunCtx& C = P.C;
+    const DevScoring& sc = C.sc;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
     const DpxConst<DUAL> K(sc);
     const uint32_t extSel = DUAL ? 0xB391u : 0x4341u;                  // int8 (signed / unsigned) -> int16
+    int32_t* table = C.page_tables + (int64_t)blockIdx.x * C.max_pages_per_task;
+    int pending = -1;
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) { sh_task = atomicAdd(P.counter, 1); sh_stop = INT32_MAX; }
+        if (tid == 0) { sh_task = next_task(C, P.Q, table, pending); sh_stop = INT32_MAX; }
         __syncthreads();
-        const int slot = sh_task;
-        if (slot >= P.n_order) return;
-        const int ti = P.order[slot];
-        const DevTask T = P.tasks[ti];
-        const int qlen = T.qlen, tlen = T.tlen, w = T.w, flag = T.flag;
-        const uint8_t* query = P.qarena + T.q_off;
-        const uint8_t* target = P.tarena + T.t_off;
-        uint8_t* tb = TB ? P.tb + T.tb_off : nullptr;
+        const int ti = sh_task;
+        if (ti < 0) return;
+        const DevTask T = C.tasks[ti];
+        const int qlen = T.qlen, tlen = T.tlen, w = T.w;
+        const uint8_t* query = C.qarena + T.q_off;
+        const uint8_t* target = C.tarena + T.t_off;
+        // traceback rows live in pool pages: row r is in page r / rows_per_page
+        int tb_rip = 0, tb_pg = 0;                 // row inside the current page, page number
+        uint8_t* tb_page = TB ? C.pool.base + (int64_t)table[0] * C.pool.page_bytes : nullptr;
         const int n_diag = qlen + tlen - 1;
 
         uint32_t U[8], V[8], X[8], Y[8], X2[8], Y2[8], S[8], Hr[8];
@@ -342,7 +339,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                     const uint32_t X2T0 = DUAL ? prmt(nbX2, X2[7], 0x5432u) : 0;
                     uint4 o;
                     dpx_cells<DUAL, TB>(U, V, X, Y, X2, Y2, S, XT0, VT0, X2T0, K, o);
-                    if (TB) *reinterpret_cast<uint4*>(tb + (int64_t)r * T.pitch + (base - st)) = o;
+                    if (TB) *reinterpret_cast<uint4*>(tb_page + (int64_t)tb_rip * T.pitch + (base - st)) = o;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {            // H[t] += v[t] - qe (:239-241)
                         uint32_t dv = prmt(V[k], 0u, extSel);
@@ -416,7 +413,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                             }
                             XT0 = (XT0 & 0xffff0000u) | x1; VT0 = (VT0 & 0xffff0000u) | v1; X2T0 = (X2T0 & 0xffff0000u) | x21;
                             if (!DUAL) {   // _mm_cvtsi32_si128(int8_t) sign-extends a negative carry into lanes 1..3 (:146-147)
-                                if (x1 & 0x8000u) { X[0] = (X[0] & 0xffff0000u) | 0xff00u | C::cE; X[1] = (X[1] & 0xffff0000u) | 0xff00u | C::cE; X[2] = (X[2] & 0xffff0000u) | 0xff00u | C::cE; }
+                                if (x1 & 0x8000u) { X[0] = (X[0] & 0xffff0000u) | 0xff00u | KC::cE; X[1] = (X[1] & 0xffff0000u) | 0xff00u | KC::cE; X[2] = (X[2] & 0xffff0000u) | 0xff00u | KC::cE; }
                                 if (v1 & 0x8000u) { V[0] = (V[0] & 0xffff0000u) | 0xff00u; V[1] = (V[1] & 0xffff0000u) | 0xff00u; V[2] = (V[2] & 0xffff0000u) | 0xff00u; }
                             }
                         }
@@ -436,7 +433,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
 
                         uint4 o;
                         dpx_cells<DUAL, TB>(U, V, X, Y, X2, Y2, S, XT0, VT0, X2T0, K, o);
-                        if (TB) *reinterpret_cast<uint4*>(tb + (int64_t)r * T.pitch + (base - st)) = o;
+                        if (TB) *reinterpret_cast<uint4*>(tb_page + (int64_t)tb_rip * T.pitch + (base - st)) = o;
 
                         // exact max bookkeeping (:224-260): H[t] += v[t] - qe ; H[en0] from its left neighbour
                         int32_t fixv = 0;
@@ -485,6 +482,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                 const int32_t wmax = __reduce_max_sync(FULL, habs);
                 if (lane == 0) sh_mh[s3][warp] = wmax;
                 last_st = st; last_en = en;
+                if (TB && ++tb_rip == T.rows_per_page) { tb_rip = 0; ++tb_pg; if (tb_pg < T.tb_pages) tb_page = C.pool.base + (int64_t)table[tb_pg] * C.pool.page_bytes; }
             }
             // ---- (D) the one barrier of the antidiagonal
             if (NW > 1) __syncthreads(); else __syncwarp();
@@ -493,22 +491,10 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
         }
         if (!dropped && stop_r < n_diag) ez.zdropped = 1;      // band exhausted (:111-114)
 
-        if (tid == 0) {   // end point and result (:292-301)
-            DevAux A; A.i0 = -1; A.j0 = -1; A.n_cigar = 0; A.pad_ = 0;
-            int reach_end = 0;
-            if (TB) {
-                if (!ez.zdropped && !(flag & FSV_EZ_EXTZ_ONLY)) { A.i0 = tlen - 1; A.j0 = qlen - 1; }
-                else if (!ez.zdropped && (flag & FSV_EZ_EXTZ_ONLY) && ez.mqe + T.end_bonus > ez.max) {
-                    reach_end = 1; A.i0 = ez.mqe_t; A.j0 = qlen - 1;
-                } else if (ez.max_t >= 0 && ez.max_q >= 0) { A.i0 = ez.max_t; A.j0 = ez.max_q; }
-            }
-            fsv_result R;
-            R.max = ez.max; R.zdropped = ez.zdropped; R.max_q = ez.max_q; R.max_t = ez.max_t;
-            R.mqe = ez.mqe; R.mqe_t = ez.mqe_t; R.mte = ez.mte; R.mte_q = ez.mte_q; R.score = ez.score;
-            R.reach_end = reach_end; R.n_cigar = 0; R.status = 0; R.cigar_off = 0; R.cells = cells;
-            P.results[T.orig] = R;
-            P.aux[ti] = A;
-        }
+        __syncthreads();             // every traceback row is written
+        if (warp == 0) finish_task(C, T, table, ez, cells, TB);
+        __syncthreads();
+        if (tid == 0) pool_free(C.pool, T.tb_pages, table);
     }
 }
 
@@ -537,39 +523,61 @@ inline bool dpx_supports(const DevScoring& sc, const DevTask& t, bool has_wild)
     return dpx_class_of(dpx_warps_needed(t)) != 0;
 }
 
+// CTAs to launch for n_tasks tasks of the NW-warp class (persistent CTAs, a whole number of waves)
 template <bool DUAL, bool TB, int NW>
-inline int dpx_launch_one(cudaStream_t stream, int sm_count, const DpxParams& P, std::string* err)
+inline int dpx_grid_one(int sm_count, int n_tasks)
 {
-    auto kern = fsv_fill_dpx_kernel<DUAL, TB, NW>;
     int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, 0);
-    if (e != cudaSuccess) { if (err) *err = cudaGetErrorString(e); cudaGetLastError(); return FSV_ERR_CUDA; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fsv_fill_dpx_kernel<DUAL, TB, NW>, NW * 32, 0) != cudaSuccess) { cudaGetLastError(); per_sm = 1; }
     if (per_sm < 1) per_sm = 1;
-    int grid = std::min(P.n_order, sm_count * per_sm);
-    kern<<<grid, NW * 32, 0, stream>>>(P);
-    e = cudaGetLastError();
+    return std::max(1, std::min(n_tasks, sm_count * per_sm));
+}
+
+template <bool DUAL, bool TB, int NW>
+inline int dpx_launch_one(cudaStream_t stream, int grid, const DpxParams& P, std::string* err)
+{
+    fsv_fill_dpx_kernel<DUAL, TB, NW><<<grid, NW * 32, 0, stream>>>(P);
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { if (err) *err = cudaGetErrorString(e); return FSV_ERR_CUDA; }
     return FSV_OK;
 }
 
-template <bool DUAL, bool TB>
-inline int dpx_launch_nw(cudaStream_t stream, int sm_count, int nw, const DpxParams& P, std::string* err)
-{
-    switch (nw) {
-        case 1: return dpx_launch_one<DUAL, TB, 1>(stream, sm_count, P, err);
-        case 2: return dpx_launch_one<DUAL, TB, 2>(stream, sm_count, P, err);
-        case 4: return dpx_launch_one<DUAL, TB, 4>(stream, sm_count, P, err);
-        case 6: return dpx_launch_one<DUAL, TB, 6>(stream, sm_count, P, err);
-        case 8: return dpx_launch_one<DUAL, TB, 8>(stream, sm_count, P, err);
+#define FSV_DPX_DISPATCH(CALL)                                                    \
+    switch (nw) {                                                                 \
+        case 1: return CALL(1);                                                   \
+        case 2: return CALL(2);                                                   \
+        case 4: return CALL(4);                                                   \
+        case 6: return CALL(6);                                                   \
+        case 8: return CALL(8);                                                   \
     }
+
+template <bool DUAL, bool TB>
+inline int dpx_grid_nw(int sm_count, int nw, int n_tasks)
+{
+#define FSV_G(N) dpx_grid_one<DUAL, TB, N>(sm_count, n_tasks)
+    FSV_DPX_DISPATCH(FSV_G)
+#undef FSV_G
+    return 1;
+}
+template <bool DUAL, bool TB>
+inline int dpx_launch_nw(cudaStream_t stream, int nw, int grid, const DpxParams& P, std::string* err)
+{
+#define FSV_L(N) dpx_launch_one<DUAL, TB, N>(stream, grid, P, err)
+    FSV_DPX_DISPATCH(FSV_L)
+#undef FSV_L
     return FSV_ERR_INVALID;
 }
 
-// one launch per (warps-per-task class, with/without traceback); `order` holds n tasks of that class
-inline int dpx_launch(cudaStream_t stream, int sm_count, bool dual, bool with_tb, int nw, const DpxParams& P, std::string* err)
+// one launch per (warps-per-task class, with/without traceback)
+inline int dpx_grid(int sm_count, bool dual, bool with_tb, int nw, int n_tasks)
 {
-    if (dual) return with_tb ? dpx_launch_nw<true, true>(stream, sm_count, nw, P, err) : dpx_launch_nw<true, false>(stream, sm_count, nw, P, err);
-    return with_tb ? dpx_launch_nw<false, true>(stream, sm_count, nw, P, err) : dpx_launch_nw<false, false>(stream, sm_count, nw, P, err);
+    if (dual) return with_tb ? dpx_grid_nw<true, true>(sm_count, nw, n_tasks) : dpx_grid_nw<true, false>(sm_count, nw, n_tasks);
+    return with_tb ? dpx_grid_nw<false, true>(sm_count, nw, n_tasks) : dpx_grid_nw<false, false>(sm_count, nw, n_tasks);
+}
+inline int dpx_launch(cudaStream_t stream, bool dual, bool with_tb, int nw, int grid, const DpxParams& P, std::string* err)
+{
+    if (dual) return with_tb ? dpx_launch_nw<true, true>(stream, nw, grid, P, err) : dpx_launch_nw<true, false>(stream, nw, grid, P, err);
+    return with_tb ? dpx_launch_nw<false, true>(stream, nw, grid, P, err) : dpx_launch_nw<false, false>(stream, nw, grid, P, err);
 }
 
 }  // namespace fsv

@@ -10,6 +10,7 @@
 // Follows software/hifiasm-0.16.1/ksw2_extz2_sse.c:101-289 lane by lane; the
 // dual-affine branch follows the restatement documented in DESIGN.md §3.
 #pragma once
+#include "fsv_backtrack.cuh"
 #include "fsv_common.cuh"
 
 namespace fsv {
@@ -19,19 +20,11 @@ constexpr int EXACT_WARPS = EXACT_THREADS / 32;
 constexpr int EXACT_NARR = 10;  // u v[2] x[2] y x2[2] y2 s
 
 struct FillParams {
-    const uint8_t* qarena;
-    const uint8_t* tarena;
-    const DevTask* tasks;
-    const int32_t* order;    // task indices, largest first
-    int32_t n_order;
-    int32_t* counter;        // work-stealing cursor
-    fsv_result* results;     // indexed by DevTask::orig
-    DevAux* aux;             // indexed by position in `tasks`
-    uint8_t* tb;             // traceback arena
+    RunCtx C;
+    TaskQueue Q;
     uint8_t* ws;             // per-CTA global window for tasks whose band exceeds shared memory
     int64_t ws_lanes;        // lanes per array in that window (power of two), 0 = none
     int32_t smem_lanes;      // lanes per array of the shared-memory window (power of two)
-    DevScoring sc;
 };
 
 __device__ __forceinline__ int s8(int x) { return (int)(int8_t)(uint8_t)x; }
@@ -64,38 +57,31 @@ __global__ void __launch_bounds__(EXACT_THREADS) fsv_fill_exact_kernel(const Fil
     __shared__ int32_t sh_task;
     __shared__ int32_t sh_part_h[2][EXACT_WARPS];
     __shared__ uint32_t sh_part_k[2][EXACT_WARPS];
-    const DevScoring& sc = P.sc;
+    const RunCtx& C = P.C;
+    const DevScoring& sc = C.sc;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int32_t* table = C.page_tables + (int64_t)blockIdx.x * C.max_pages_per_task;
+    int pending = -1;
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) sh_task = atomicAdd(P.counter, 1);
+        if (tid == 0) sh_task = next_task(C, P.Q, table, pending);
         __syncthreads();
-        const int slot = sh_task;
-        if (slot >= P.n_order) return;
-        const int ti = P.order[slot];
-        const DevTask T = P.tasks[ti];
+        const int ti = sh_task;
+        if (ti < 0) return;
+        const DevTask T = C.tasks[ti];
         EzState ez; ez.reset();
         int64_t cells = 0;
-        int status = 0;
         if (T.kind == 0) {           // ksw2's silent returns (ksw2_extz2_sse.c:57,82)
-            if (tid == 0) {
-                fsv_result R;
-                R.max = 0; R.zdropped = 0; R.max_q = R.max_t = R.mqe_t = R.mte_q = -1;
-                R.mqe = R.mte = R.score = FSV_NEG_INF; R.reach_end = 0; R.n_cigar = 0;
-                R.status = T.pad_; R.cigar_off = 0; R.cells = 0;
-                P.results[T.orig] = R;
-                DevAux A; A.i0 = -1; A.j0 = -1; A.n_cigar = 0; A.pad_ = 0; P.aux[ti] = A;
-            }
+            if (tid == 0) finish_reset_task(C, T);
             continue;
         }
         const int qlen = T.qlen, tlen = T.tlen, w = T.w, flag = T.flag;
         const bool with_cigar = !(flag & FSV_EZ_SCORE_ONLY), right = (flag & FSV_EZ_RIGHT) != 0;
         const bool approx = (flag & FSV_EZ_APPROX_MAX) != 0, generic = (flag & FSV_EZ_GENERIC_SC) != 0;
         const int L = (tlen + 15) / 16 * 16;
-        const uint8_t* query = P.qarena + T.q_off;
-        const uint8_t* target = P.tarena + T.t_off;
-        uint8_t* tb = with_cigar ? P.tb + T.tb_off : nullptr;
+        const uint8_t* query = C.qarena + T.q_off;
+        const uint8_t* target = C.tarena + T.t_off;
 
         // lane window: shared memory when the band fits, else this CTA's global slice
         LaneWindow W;
@@ -131,6 +117,7 @@ __global__ void __launch_bounds__(EXACT_THREADS) fsv_fill_exact_kernel(const Fil
                 __syncthreads();
             }
             const int store_end = st0 + ((en0 - st0) / 16) * 16 + 15;  // last lane the profile stores touch (:126-140)
+            uint8_t* tbrow = with_cigar ? tb_row(C.pool, table, T.rows_per_page, T.pitch, r) : nullptr;
             const uint8_t* xin = W.x[par]; const uint8_t* vin = W.v[par]; const uint8_t* x2in = W.x2[par];
             uint8_t* xout = W.x[par ^ 1]; uint8_t* vout = W.v[par ^ 1]; uint8_t* x2out = W.x2[par ^ 1];
             // carries into the first lane (:118-122)
@@ -238,7 +225,7 @@ __global__ void __launch_bounds__(EXACT_THREADS) fsv_fill_exact_kernel(const Fil
                 }
                 W.u[k] = (uint8_t)un; vout[k] = (uint8_t)vn; xout[k] = (uint8_t)xn; W.y[k] = (uint8_t)yn;
                 if (DUAL) { x2out[k] = (uint8_t)x2n; W.y2[k] = (uint8_t)y2n; }
-                if (with_cigar) tb[(int64_t)r * T.pitch + (t - st)] = (uint8_t)d;
+                if (with_cigar) tbrow[t - st] = (uint8_t)d;
             }
             __syncthreads();   // A: every lane of this antidiagonal is in the window
 
@@ -301,22 +288,10 @@ __global__ void __launch_bounds__(EXACT_THREADS) fsv_fill_exact_kernel(const Fil
             last_st = st; last_en = en; par ^= 1;
         }
 
-        if (tid == 0) {   // end point and result (:292-301)
-            DevAux A; A.i0 = -1; A.j0 = -1; A.n_cigar = 0; A.pad_ = 0;
-            int reach_end = 0;
-            if (with_cigar) {
-                if (!ez.zdropped && !(flag & FSV_EZ_EXTZ_ONLY)) { A.i0 = tlen - 1; A.j0 = qlen - 1; }
-                else if (!ez.zdropped && (flag & FSV_EZ_EXTZ_ONLY) && ez.mqe + T.end_bonus > ez.max) {
-                    reach_end = 1; A.i0 = ez.mqe_t; A.j0 = qlen - 1;
-                } else if (ez.max_t >= 0 && ez.max_q >= 0) { A.i0 = ez.max_t; A.j0 = ez.max_q; }
-            }
-            fsv_result R;
-            R.max = ez.max; R.zdropped = ez.zdropped; R.max_q = ez.max_q; R.max_t = ez.max_t;
-            R.mqe = ez.mqe; R.mqe_t = ez.mqe_t; R.mte = ez.mte; R.mte_q = ez.mte_q; R.score = ez.score;
-            R.reach_end = reach_end; R.n_cigar = 0; R.status = status; R.cigar_off = 0; R.cells = cells;
-            P.results[T.orig] = R;
-            P.aux[ti] = A;
-        }
+        __syncthreads();             // every traceback row is written
+        if (warp == 0) finish_task(C, T, table, ez, cells, with_cigar);
+        __syncthreads();
+        if (tid == 0) pool_free(C.pool, T.tb_pages, table);
     }
 }
 
