@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(_HERE, "libfocalsv_cuda.so")
 EXPORTS = ("fsv_init", "fsv_destroy", "fsv_strerror", "fsv_last_error", "fsv_abi_version", "fsv_device_count",
            "fsv_get_stats", "fsv_set_option", "fsv_align_batch", "fsv_batch_create", "fsv_batch_run",
            "fsv_batch_fetch", "fsv_batch_destroy", "fsv_ksw_extz2", "fsv_ksw_extd2", "fsv_task_cells",
-           "fsv_lpt_bins", "fsv_measure_int_peak")
+           "fsv_lpt_bins", "fsv_measure_int_peak", "fsv_batch_timeline")
 
 _lib = None
 
@@ -56,6 +56,7 @@ def load_library(path=None):
     lib.fsv_batch_run.argtypes = [vp]
     lib.fsv_batch_fetch.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
     lib.fsv_batch_destroy.argtypes = [vp]
+    lib.fsv_batch_timeline.argtypes = [vp, vp]
     lib.fsv_batch_destroy.restype = None
     lib.fsv_task_cells.argtypes = [i32, i32, i32]
     lib.fsv_task_cells.restype = i64
@@ -216,6 +217,12 @@ class Batch(object):
         rc = self._lib.fsv_batch_fetch(self._h, out.ctypes.data, cig.ctypes.data, int(cigar_cap), C.byref(used))
         self._al._check(rc, "fsv_batch_fetch")
         return out, cig[:used.value]
+
+    def timeline(self):
+        """(n, 2) int64: device start / end time (ns) of every task in the last run."""
+        out = np.zeros((len(self.tasks), 2), dtype=np.int64)
+        self._al._check(self._lib.fsv_batch_timeline(self._h, out.ctypes.data), "fsv_batch_timeline")
+        return out
 
     def close(self):
         if getattr(self, "_h", None):

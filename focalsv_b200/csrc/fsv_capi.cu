@@ -29,7 +29,7 @@ struct fsv_ctx {
     int sm_count = 0;
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;            // copies, timing events
-    cudaStream_t kstream[12] = {};            // one per concurrently running fill-kernel variant
+    cudaStream_t kstream[16] = {};            // one per concurrently running fill-kernel variant
     std::string last_error;
     fsv_stats stats{};
     // options
@@ -45,7 +45,7 @@ struct fsv_ctx {
 };
 
 // one fill-kernel launch: a slice of the work list, largest task first
-struct Launch { int kind /*0 general, 1 DPX*/, nw, with_tb, begin, count, grid; int64_t table_off; };
+struct Launch { int kind /*0 general, 1 DPX*/, nw, with_tb, excl, begin, count, grid; int64_t table_off; };
 
 // any base code outside A,C,G,T (0..3)?  8 bytes at a time.
 static bool has_wildcard(const uint8_t* p, size_t n)
@@ -80,6 +80,7 @@ struct fsv_batch {
     int32_t* d_ctrl = nullptr;        // [0] overflow flag, [1] pool lock, [2] pool n_free; [8..] queue states (8 B each)
     unsigned long long* d_cursor = nullptr;
     uint32_t* d_cigar = nullptr;
+    long long* d_timeline = nullptr;
     int state = 0;                    // 0 created, 1 run
 };
 
@@ -254,7 +255,7 @@ static int64_t pow2_at_least(int64_t x) { int64_t p = 1; while (p < x) p <<= 1; 
 static void free_batch_device(fsv_batch* b)
 {
     cudaFree(b->d_q); cudaFree(b->d_t); cudaFree(b->d_tasks); cudaFree(b->d_work); cudaFree(b->d_results);
-    cudaFree(b->d_ctrl); cudaFree(b->d_cursor); cudaFree(b->d_cigar);
+    cudaFree(b->d_ctrl); cudaFree(b->d_cursor); cudaFree(b->d_cigar); cudaFree(b->d_timeline);
 }
 
 extern "C" void fsv_batch_destroy(fsv_batch* b)
@@ -352,7 +353,7 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
             size_t fr = 0, tot = 0;
             CK(c, cudaMemGetInfo(&fr, &tot));
             fr += c->pool_cap;                       // the pool of a previous batch is reused
-            budget = (int64_t)(fr * 0.70);
+            budget = (int64_t)(fr * 0.88) - (int64_t)(cigar_words * 4);   // leave room for the CIGAR arena and the sequences
         }
         int64_t cap_pages = std::max<int64_t>(budget / c->page_bytes, 0);
         b->pool_pages = std::min(pages_total, cap_pages);
@@ -369,29 +370,50 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
     std::vector<int32_t> ord(n);
     for (size_t i = 0; i < n; ++i) ord[i] = (int32_t)i;
     std::stable_sort(ord.begin(), ord.end(), [&](int32_t a, int32_t x) { return b->tasks[a].cells_est > b->tasks[x].cells_est; });
+    // The few tasks that are long enough to decide the batch time by themselves get an SM each
+    // ("exclusive" launch, started first): a CTA that shares its SM runs each antidiagonal about
+    // twice as slowly, and nothing can shorten a task's chain of antidiagonals.
+    std::vector<uint8_t> is_excl(n, 0);
+    {
+        const double t_solo = 1.5e-6, t_shared = 2.8e-6, dev_cups = 4.0e11;      // per antidiagonal / per cell (planning only)
+        double cells_sum = 0, longest = 0;
+        for (size_t i = 0; i < n; ++i) if (b->is_dpx[i]) {
+            cells_sum += (double)b->tasks[i].cells_est;
+            longest = std::max(longest, (double)(b->tasks[i].qlen + b->tasks[i].tlen) * t_solo);
+        }
+        const double t_est = std::max(cells_sum / dev_cups, longest);
+        int n_excl = 0;
+        for (size_t k = 0; k < n && n_excl < c->sm_count / 4; ++k) {
+            const int ti = ord[k];
+            const DevTask& d = b->tasks[ti];
+            if (!b->is_dpx[ti] || d.nw < 6) continue;
+            if ((double)(d.qlen + d.tlen) * t_shared > 0.7 * t_est) { is_excl[ti] = 1; ++n_excl; }
+        }
+    }
     int64_t ws_need = 0, table_off = 0;
-    auto add_launch = [&](int kind, int nw, int with_tb) {
-        Launch L{kind, nw, with_tb, (int)b->work.size(), 0, 0, 0};
+    auto add_launch = [&](int kind, int nw, int with_tb, int excl) {
+        Launch L{kind, nw, with_tb, excl, (int)b->work.size(), 0, 0, 0};
         for (size_t k = 0; k < n; ++k) {
             const int ti = ord[k];
             const DevTask& d = b->tasks[ti];
             if (kind == 0) { if (b->is_dpx[ti]) continue; }
-            else if (!b->is_dpx[ti] || d.nw != nw || (int)!(d.flag & FSV_EZ_SCORE_ONLY) != with_tb) continue;
+            else if (!b->is_dpx[ti] || d.nw != nw || (int)!(d.flag & FSV_EZ_SCORE_ONLY) != with_tb || (int)is_excl[ti] != excl) continue;
             b->work.push_back(ti);
             if (kind == 0 && d.kind == 1 && d.pitch + 96 > c->exact_smem_lanes) ws_need = std::max<int64_t>(ws_need, d.pitch + 96);
         }
         L.count = (int)b->work.size() - L.begin;
         if (!L.count) return;
-        L.grid = kind == 0 ? exact_grid(c, b->dual, L.count) : dpx_grid(c->sm_count, b->dual, with_tb != 0, nw, L.count);
+        L.grid = kind == 0 ? exact_grid(c, b->dual, L.count) : excl ? L.count : dpx_grid(c->sm_count, b->dual, with_tb != 0, nw, L.count);
         L.table_off = table_off;
         table_off += (int64_t)L.grid * b->max_pages_per_task;
         b->launches.push_back(L);
     };
     static const int kClasses[5] = {8, 6, 4, 2, 1};
-    for (int cls : kClasses) for (int with_tb = 1; with_tb >= 0; --with_tb) add_launch(1, cls, with_tb);
-    add_launch(0, 0, 0);
+    for (int cls : {8, 6}) for (int with_tb = 1; with_tb >= 0; --with_tb) add_launch(1, cls, with_tb, 1);
+    for (int cls : kClasses) for (int with_tb = 1; with_tb >= 0; --with_tb) add_launch(1, cls, with_tb, 0);
+    add_launch(0, 0, 0, 0);
     b->ws_lanes = ws_need ? pow2_at_least(ws_need) : 0;
-    if (b->launches.size() > 12) { delete b; return FSV_ERR_INVALID; }
+    if (b->launches.size() > 16) { delete b; return FSV_ERR_INVALID; }
 
     // ---- device buffers + H2D
     auto fail = [&](int code) { free_batch_device(b); delete b; return code; };
@@ -412,6 +434,8 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
     CKB(cudaMalloc(&b->d_ctrl, 256));
     CKB(cudaMalloc(&b->d_cursor, 64));
     CKB(cudaMalloc(&b->d_cigar, (size_t)(b->cigar_cap_words + 4) * 4));
+    CKB(cudaMalloc(&b->d_timeline, (n + 1) * 16));
+    CKB(cudaMemsetAsync(b->d_timeline, 0, (n + 1) * 16, c->stream));
     if (qbytes) CKB(cudaMemcpyAsync(b->d_q, qarena, qbytes, cudaMemcpyHostToDevice, c->stream));
     if (tbytes) CKB(cudaMemcpyAsync(b->d_t, tarena, tbytes, cudaMemcpyHostToDevice, c->stream));
     if (n) {
@@ -471,6 +495,7 @@ extern "C" int fsv_batch_run(fsv_batch* b)
     R.pool.free_stack = c->d_free_stack; R.pool.n_free = b->d_ctrl + 2; R.pool.lock = b->d_ctrl + 1;
     R.max_pages_per_task = b->max_pages_per_task;
     R.cigar = b->d_cigar; R.cigar_cursor = b->d_cursor; R.cigar_cap = b->cigar_cap_words; R.overflow = b->d_ctrl + 0;
+    R.timeline = b->d_timeline;
     R.sc = b->sc;
 
     cudaEvent_t e0, e1;
@@ -487,7 +512,7 @@ extern "C" int fsv_batch_run(fsv_batch* b)
         R.page_tables = c->d_tables + L.table_off;
         if (L.kind == 1) {
             DpxParams D{R, Q};
-            rc = dpx_launch(ks, b->dual, L.with_tb != 0, L.nw, L.grid, D, &c->last_error);
+            rc = dpx_launch(ks, b->dual, L.with_tb != 0, L.nw, L.grid, L.excl != 0, D, &c->last_error);
             if (rc != FSV_OK) return rc;
         } else {
             FillParams P{R, Q, c->d_ws, b->ws_lanes, c->exact_smem_lanes};
@@ -538,6 +563,16 @@ extern "C" int fsv_batch_fetch(fsv_batch* b, fsv_result* out, uint32_t* cigar, s
         CK(c, cudaStreamSynchronize(c->stream));
         c->stats.d2h_bytes += used * 4;
     }
+    return FSV_OK;
+}
+
+extern "C" int fsv_batch_timeline(fsv_batch* b, int64_t* start_end_ns)
+{
+    if (!b || !start_end_ns) return FSV_ERR_INVALID;
+    fsv_ctx* c = b->ctx;
+    if (b->state != 1) return FSV_ERR_STATE;
+    CK(c, cudaSetDevice(c->device));
+    if (b->n) CK(c, cudaMemcpy(start_end_ns, b->d_timeline, b->n * 16, cudaMemcpyDeviceToHost));
     return FSV_OK;
 }
 

@@ -176,6 +176,7 @@ struct RunCtx {
     unsigned long long* cigar_cursor;
     int64_t cigar_cap;           // words
     int32_t* overflow;           // set when the arena is too small
+    long long* timeline;         // per task (caller order): start ns, end ns (globaltimer), or null
     DevScoring sc;
 };
 
@@ -200,6 +201,13 @@ __device__ inline int next_task(const RunCtx& C, const TaskQueue& Q, int32_t* ta
         if (pool_try_alloc(C.pool, C.tasks[t].tb_pages, table)) return t;
         pending = t;
     }
+}
+
+__device__ __forceinline__ long long global_ns()
+{
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
 }
 
 // byte address of traceback row r of a task (rows_per_page = page_bytes / pitch)

@@ -175,7 +175,9 @@ __device__ __forceinline__ void dpx_cells(uint32_t (&U)[8], uint32_t (&V)[8], ui
     }
 }
 
-template <bool DUAL, bool TB, int NW>
+// EXCL only tags a second copy of the 6- and 8-warp kernels: it is launched with (almost) all of an SM's
+// shared memory reserved, so that a CTA working on one of the few very long tasks has its SM to itself.
+template <bool DUAL, bool TB, int NW, bool EXCL = false>
 __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kernel(const DpxParams P)
 {
     constexpr int NT = NW * 32;
@@ -203,6 +205,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
         const int ti = sh_task;
         if (ti < 0) return;
         const DevTask T = C.tasks[ti];
+        if (tid == 0 && C.timeline) C.timeline[2 * T.orig] = global_ns();
         const int qlen = T.qlen, tlen = T.tlen, w = T.w;
         const uint8_t* query = C.qarena + T.q_off;
         const uint8_t* target = C.tarena + T.t_off;
@@ -494,7 +497,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
         __syncthreads();             // every traceback row is written
         if (warp == 0) finish_task(C, T, table, ez, cells, TB);
         __syncthreads();
-        if (tid == 0) pool_free(C.pool, T.tb_pages, table);
+        if (tid == 0) { pool_free(C.pool, T.tb_pages, table); if (C.timeline) C.timeline[2 * T.orig + 1] = global_ns(); }
     }
 }
 
@@ -523,22 +526,31 @@ inline bool dpx_supports(const DevScoring& sc, const DevTask& t, bool has_wild)
     return dpx_class_of(dpx_warps_needed(t)) != 0;
 }
 
-// CTAs to launch for n_tasks tasks of the NW-warp class (persistent CTAs, a whole number of waves)
+constexpr int DPX_EXCL_SMEM = 227 * 1024 - 512;   // dynamic shared memory reserved by an exclusive CTA: nothing else fits on its SM
+
+// CTAs to launch for n_tasks tasks of the NW-warp class (persistent CTAs)
 template <bool DUAL, bool TB, int NW>
 inline int dpx_grid_one(int sm_count, int n_tasks)
 {
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fsv_fill_dpx_kernel<DUAL, TB, NW>, NW * 32, 0) != cudaSuccess) { cudaGetLastError(); per_sm = 1; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fsv_fill_dpx_kernel<DUAL, TB, NW, false>, NW * 32, 0) != cudaSuccess) { cudaGetLastError(); per_sm = 1; }
     if (per_sm < 1) per_sm = 1;
     return std::max(1, std::min(n_tasks, sm_count * per_sm));
 }
 
 template <bool DUAL, bool TB, int NW>
-inline int dpx_launch_one(cudaStream_t stream, int grid, const DpxParams& P, std::string* err)
+inline int dpx_launch_one(cudaStream_t stream, int grid, bool excl, const DpxParams& P, std::string* err)
 {
-    fsv_fill_dpx_kernel<DUAL, TB, NW><<<grid, NW * 32, 0, stream>>>(P);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { if (err) *err = cudaGetErrorString(e); return FSV_ERR_CUDA; }
+    cudaError_t e = cudaSuccess;
+    if (excl && NW >= 6) {
+        auto kern = fsv_fill_dpx_kernel<DUAL, TB, (NW >= 6 ? NW : 6), true>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DPX_EXCL_SMEM);
+        if (e == cudaSuccess) kern<<<grid, NW * 32, DPX_EXCL_SMEM, stream>>>(P);
+    } else {
+        fsv_fill_dpx_kernel<DUAL, TB, NW, false><<<grid, NW * 32, 0, stream>>>(P);
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { if (err) *err = cudaGetErrorString(e); cudaGetLastError(); return FSV_ERR_CUDA; }
     return FSV_OK;
 }
 
@@ -560,24 +572,24 @@ inline int dpx_grid_nw(int sm_count, int nw, int n_tasks)
     return 1;
 }
 template <bool DUAL, bool TB>
-inline int dpx_launch_nw(cudaStream_t stream, int nw, int grid, const DpxParams& P, std::string* err)
+inline int dpx_launch_nw(cudaStream_t stream, int nw, int grid, bool excl, const DpxParams& P, std::string* err)
 {
-#define FSV_L(N) dpx_launch_one<DUAL, TB, N>(stream, grid, P, err)
+#define FSV_L(N) dpx_launch_one<DUAL, TB, N>(stream, grid, excl, P, err)
     FSV_DPX_DISPATCH(FSV_L)
 #undef FSV_L
     return FSV_ERR_INVALID;
 }
 
-// one launch per (warps-per-task class, with/without traceback)
+// one launch per (warps-per-task class, with/without traceback, exclusive or not)
 inline int dpx_grid(int sm_count, bool dual, bool with_tb, int nw, int n_tasks)
 {
     if (dual) return with_tb ? dpx_grid_nw<true, true>(sm_count, nw, n_tasks) : dpx_grid_nw<true, false>(sm_count, nw, n_tasks);
     return with_tb ? dpx_grid_nw<false, true>(sm_count, nw, n_tasks) : dpx_grid_nw<false, false>(sm_count, nw, n_tasks);
 }
-inline int dpx_launch(cudaStream_t stream, bool dual, bool with_tb, int nw, int grid, const DpxParams& P, std::string* err)
+inline int dpx_launch(cudaStream_t stream, bool dual, bool with_tb, int nw, int grid, bool excl, const DpxParams& P, std::string* err)
 {
-    if (dual) return with_tb ? dpx_launch_nw<true, true>(stream, nw, grid, P, err) : dpx_launch_nw<true, false>(stream, nw, grid, P, err);
-    return with_tb ? dpx_launch_nw<false, true>(stream, nw, grid, P, err) : dpx_launch_nw<false, false>(stream, nw, grid, P, err);
+    if (dual) return with_tb ? dpx_launch_nw<true, true>(stream, nw, grid, excl, P, err) : dpx_launch_nw<true, false>(stream, nw, grid, excl, P, err);
+    return with_tb ? dpx_launch_nw<false, true>(stream, nw, grid, excl, P, err) : dpx_launch_nw<false, false>(stream, nw, grid, excl, P, err);
 }
 
 }  // namespace fsv

@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(EXACT_THREADS) fsv_fill_exact_kernel(const Fil
         const int ti = sh_task;
         if (ti < 0) return;
         const DevTask T = C.tasks[ti];
+        if (tid == 0 && C.timeline) C.timeline[2 * T.orig] = global_ns();
         EzState ez; ez.reset();
         int64_t cells = 0;
         if (T.kind == 0) {           // ksw2's silent returns (ksw2_extz2_sse.c:57,82)
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(EXACT_THREADS) fsv_fill_exact_kernel(const Fil
         __syncthreads();             // every traceback row is written
         if (warp == 0) finish_task(C, T, table, ez, cells, with_cigar);
         __syncthreads();
-        if (tid == 0) pool_free(C.pool, T.tb_pages, table);
+        if (tid == 0) { pool_free(C.pool, T.tb_pages, table); if (C.timeline) C.timeline[2 * T.orig + 1] = global_ns(); }
     }
 }
 

@@ -151,6 +151,9 @@ int fsv_batch_run(fsv_batch* batch);
 int fsv_batch_fetch(fsv_batch* batch, fsv_result* out,
                     uint32_t* cigar_arena, size_t cigar_cap, size_t* cigar_used);
 void fsv_batch_destroy(fsv_batch* batch);
+/* Per-task device timeline of the last run (GPU globaltimer, ns): start_end_ns[2*i] = when task i got its
+ * traceback pages and started, [2*i+1] = when its CIGAR was written.  For schedule analysis / tracing. */
+int fsv_batch_timeline(fsv_batch* batch, int64_t* start_end_ns);
 
 /* ---- single-task convenience, argument-for-argument ksw2.h:54-61 ------
  * (km dropped; ez -> fsv_result + caller-owned cigar buffer). */

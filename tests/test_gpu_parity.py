@@ -195,8 +195,9 @@ def test_full_size_properties_cfg2_slice(oracle, aligner):
         assert np.array_equal(res[f], res2[f])
         if f != "n_cigar":
             assert np.array_equal(res[f], res3[f]), f
-    assert np.array_equal(cig, cig2)
     from focalsv_b200 import api
+    for i in range(len(res)):          # the arena order depends on completion order; per-task CIGARs do not
+        assert np.array_equal(task_cigar(res[i], cig), task_cigar(res2[i], cig2))
     n_ok = 0
     for i, t in enumerate(g.tasks):
         q = g.qarena[t["q_off"]:t["q_off"] + t["qlen"]]
