@@ -1,0 +1,131 @@
+"""Pipeline hook: (contig, reference window) pairs in, alignment records and per-contig SV signatures out.
+
+This is the host-side mirror of the step FocalSV performs around its minimap2 call
+(focalsv/4_sv_calling/Dippav/DipPAV_variant_call.py:97-137): align every haplotype contig of a
+region against that region's reference window, then walk each CIGAR for DEL/INS signatures
+(extract_contig_signature_CCS.py:14-127, `extract_sig_from_cigar`).  The alignment itself is
+`Aligner.align_batch` (libfocalsv_cuda); this module only shapes inputs and outputs so that the
+reference's consumers see what they read from pysam today: reference_name, pos, cigar tuples,
+qname, is_reverse, mapq.
+
+Next-row scope: the signature extraction below is the reference's per-read rule set
+restated in a few lines of Python; clustering across contigs / genotype pairing stay in the
+reference's own code, which consumes these records unchanged.
+"""
+from collections import namedtuple
+
+import numpy as np
+
+from . import _abi
+from .api import make_tasks, task_cigar
+from .presets import PRESETS, ksw_band, scoring_for
+
+AlignedContig = namedtuple("AlignedContig", "qname reference_name pos reference_end cigar is_reverse mapq query_length score zdropped")
+Signature = namedtuple("Signature", "chrom svtype pos svlen qname read_start read_end strand source mapq")
+
+_CODE = np.full(256, 4, dtype=np.uint8)
+for _i, _c in enumerate("ACGT"):
+    _CODE[ord(_c)] = _i
+    _CODE[ord(_c.lower())] = _i
+
+
+def encode(seq):
+    """ASCII bases -> codes 0..3, everything else 4 (Correct.cpp:7676-7685 convention)."""
+    if isinstance(seq, np.ndarray) and seq.dtype == np.uint8 and (seq.size == 0 or seq.max() <= 4):
+        return seq
+    if isinstance(seq, str):
+        seq = seq.encode()
+    return _CODE[np.frombuffer(bytes(seq), dtype=np.uint8)]
+
+
+def cigar_tuples(words):
+    """BAM-encoded words -> pysam-style [(op, len), ...]."""
+    return [(int(w) & 0xF, int(w) >> 4) for w in words]
+
+
+def realign_regions(aligner, windows, contigs, preset="asm5", bw=2000, flag=0):
+    """Align contig i against window i (same region) on the GPU.
+
+    windows: list of (chrom, start, sequence); contigs: list of (qname, sequence).
+    Scoring / z-drop are the preset's (presets.py); the band is minimap2's bw*1.5+1 for `-r{bw}`
+    (DipPAV_variant_call.py:103 passes -r2k).  Returns one AlignedContig per pair."""
+    p = PRESETS[preset]
+    sc = scoring_for(preset)
+    q = [encode(s) for _, s in contigs]
+    t = [encode(s) for _, _, s in windows]
+    tasks = make_tasks([len(x) for x in q], [len(x) for x in t], ksw_band(bw), p.zdrop, 0, flag)
+    qa = np.concatenate(q) if q else np.zeros(0, np.uint8)
+    ta = np.concatenate(t) if t else np.zeros(0, np.uint8)
+    res, arena = aligner.align_batch(sc, qa, ta, tasks)
+    return records_from_results(windows, contigs, res, arena)
+
+
+def records_from_results(windows, contigs, res, arena):
+    out = []
+    for i, ((chrom, start, _), (qname, qseq)) in enumerate(zip(windows, contigs)):
+        cig = cigar_tuples(task_cigar(res[i], arena))
+        ref_span = sum(n for op, n in cig if op in (0, 2))
+        out.append(AlignedContig(qname, chrom, int(start), int(start) + ref_span, cig, False, 60, len(qseq),
+                                 int(res[i]["score"]), bool(res[i]["zdropped"])))
+    return out
+
+
+def _merge_runs(sigs, rule):
+    """Fold neighbouring signatures of one contig left to right with `rule(prev, cur) -> merged | None`."""
+    if len(sigs) < 2:
+        return sigs
+    out = [sigs[0]]
+    for cur in sigs[1:]:
+        m = rule(out[-1], cur)
+        if m is None:
+            out.append(cur)
+        else:
+            out[-1] = m
+    return out
+
+
+def extract_sig_from_cigar(rec, min_svlen=30):
+    """DEL / INS signatures of one aligned contig (extract_contig_signature_CCS.py:14-127).
+
+    CIGAR walk: D >= min_svlen -> DEL at the reference offset; I >= min_svlen -> INS; soft clips advance
+    the contig offset, a leading hard clip shifts contig coordinates.  Then, per contig, neighbouring INS
+    are merged when both are long and close (>250 bp within 250 bp; >320 within 380; >100 within 250) and
+    neighbouring DEL when both >150 bp start within 150 bp.  Returns (dels, inss, ref_end, contig_end)."""
+    strand = "-" if rec.is_reverse else "+"
+    hard = rec.cigar[0][1] if rec.cigar and rec.cigar[0][0] == 5 else 0
+    ro, co = rec.pos, 0
+    dels, inss = [], []
+    for op, n in rec.cigar:
+        if op == 0:
+            ro += n; co += n
+        elif op == 4:
+            co += n
+        elif op == 2:
+            if n >= min_svlen:
+                dels.append(Signature(rec.reference_name, "DEL", ro, n, rec.qname, co + hard, co + hard + 1, strand, "cigar", rec.mapq))
+            ro += n
+        elif op == 1:
+            if n >= min_svlen:
+                inss.append(Signature(rec.reference_name, "INS", ro, n, rec.qname, co + hard, co + hard + n, strand, "cigar", rec.mapq))
+            co += n
+
+    def ins_rule(a, b):
+        near = abs(b.pos - a.pos)
+        ok = (a.svlen > 250 and b.svlen > 250 and near < 250) or (a.svlen > 320 and b.svlen > 320 and near < 380) or \
+             (a.svlen > 100 and b.svlen > 100 and near < 250)
+        return a._replace(svlen=b.read_end - a.read_start, read_end=b.read_end) if ok else None
+
+    def del_rule(a, b):
+        ok = a.svlen > 150 and b.svlen > 150 and abs(b.pos - a.pos) < 150
+        return a._replace(svlen=b.pos + b.svlen - a.pos, read_end=a.read_start + 1) if ok else None
+
+    return _merge_runs(dels, del_rule), _merge_runs(inss, ins_rule), ro, co
+
+
+def signatures(records, min_svlen=30):
+    """All DEL/INS signatures of a list of AlignedContig, in record order."""
+    out = []
+    for r in records:
+        d, i, _, _ = extract_sig_from_cigar(r, min_svlen)
+        out.extend(d); out.extend(i)
+    return out

@@ -16,7 +16,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "_ref")
 REF_DIR = "/root/reference/software/hifiasm-0.16.1"
-CFLAGS = ["-O3", "-msse4.1", "-fPIC", "-shared", "-fno-strict-aliasing", "-pthread"]
+CFLAGS = ["-O3", "-msse4.1", "-std=gnu11", "-fPIC", "-shared", "-fno-strict-aliasing", "-pthread"]
 
 
 def _stale(target, sources):

@@ -384,6 +384,78 @@ int fsvo_extz2(int qlen, const uint8_t* query, int tlen, const uint8_t* target, 
     return emit_cigar(ez, &cg, cigar, cigar_cap);
 }
 
+
+/* ---------------------------------------------------------------------- */
+/* The same dual-affine lane arithmetic as the loop in fsvo_extd2, written so that gcc vectorises it
+ * (16 int8 lanes per SSE register, like the reference's own SSE build): the t-1 operands are first
+ * copied into shifted scratch rows, then every lane is independent.  Used when no diagnostics are
+ * requested; tests/test_oracle_fast_path.py checks it lane for lane against the scalar loop. */
+typedef int8_t i8;
+#define SMAX(a, b) ((a) > (b) ? (a) : (b))
+static void extd2_row_fast(int n, i8* restrict u, i8* restrict v, i8* restrict x, i8* restrict y, i8* restrict x2,
+                           i8* restrict y2, const i8* restrict s, uint8_t* restrict pr, i8 x1, i8 x21, i8 v1,
+                           i8 q_, i8 q2_, i8 qe_, i8 qe2_, i8 mch, int mode,
+                           i8* restrict xt, i8* restrict vt, i8* restrict x2t)
+{
+    int i;
+    xt[0] = x1; vt[0] = v1; x2t[0] = x21;
+    if (n > 1) { memcpy(xt + 1, x, (size_t)n - 1); memcpy(vt + 1, v, (size_t)n - 1); memcpy(x2t + 1, x2, (size_t)n - 1); }
+    if (mode == 0) {            /* score only */
+        for (i = 0; i < n; ++i) {
+            i8 ut = u[i], vt1 = vt[i];
+            i8 a = (i8)(xt[i] + vt1), b = (i8)(y[i] + ut), a2 = (i8)(x2t[i] + vt1), b2 = (i8)(y2[i] + ut);
+            i8 z = s[i], t1, t2;
+            z = SMAX(z, a); z = SMAX(z, b); z = SMAX(z, a2); z = SMAX(z, b2);
+            z = z < mch ? z : mch;
+            u[i] = (i8)(z - vt1); v[i] = (i8)(z - ut);
+            t1 = (i8)(z - q_); t2 = (i8)(z - q2_);
+            a = (i8)(a - t1); b = (i8)(b - t1); a2 = (i8)(a2 - t2); b2 = (i8)(b2 - t2);
+            x[i] = (i8)(SMAX(a, 0) - qe_); y[i] = (i8)(SMAX(b, 0) - qe_);
+            x2[i] = (i8)(SMAX(a2, 0) - qe2_); y2[i] = (i8)(SMAX(b2, 0) - qe2_);
+        }
+    } else if (mode == 1) {     /* CIGAR, gaps left-aligned: ties H > E > F > E2 > F2 */
+        for (i = 0; i < n; ++i) {
+            i8 ut = u[i], vt1 = vt[i];
+            i8 a = (i8)(xt[i] + vt1), b = (i8)(y[i] + ut), a2 = (i8)(x2t[i] + vt1), b2 = (i8)(y2[i] + ut);
+            i8 z = s[i], t1, t2;
+            uint8_t d;
+            d = a > z ? 1 : 0;   z = SMAX(z, a);
+            d = b > z ? 2 : d;   z = SMAX(z, b);
+            d = a2 > z ? 3 : d;  z = SMAX(z, a2);
+            d = b2 > z ? 4 : d;  z = SMAX(z, b2);
+            z = z < mch ? z : mch;
+            u[i] = (i8)(z - vt1); v[i] = (i8)(z - ut);
+            t1 = (i8)(z - q_); t2 = (i8)(z - q2_);
+            a = (i8)(a - t1); b = (i8)(b - t1); a2 = (i8)(a2 - t2); b2 = (i8)(b2 - t2);
+            d |= a > 0 ? 0x08 : 0;  d |= b > 0 ? 0x10 : 0;  d |= a2 > 0 ? 0x20 : 0;  d |= b2 > 0 ? 0x40 : 0;
+            x[i] = (i8)(SMAX(a, 0) - qe_); y[i] = (i8)(SMAX(b, 0) - qe_);
+            x2[i] = (i8)(SMAX(a2, 0) - qe2_); y2[i] = (i8)(SMAX(b2, 0) - qe2_);
+            pr[i] = d;
+        }
+    } else {                    /* CIGAR, gaps right-aligned: ties F2 > E2 > F > E > H */
+        for (i = 0; i < n; ++i) {
+            i8 ut = u[i], vt1 = vt[i];
+            i8 a = (i8)(xt[i] + vt1), b = (i8)(y[i] + ut), a2 = (i8)(x2t[i] + vt1), b2 = (i8)(y2[i] + ut);
+            i8 z = s[i], t1, t2;
+            uint8_t d;
+            d = z > a ? 0 : 1;   z = SMAX(z, a);
+            d = z > b ? d : 2;   z = SMAX(z, b);
+            d = z > a2 ? d : 3;  z = SMAX(z, a2);
+            d = z > b2 ? d : 4;  z = SMAX(z, b2);
+            z = z < mch ? z : mch;
+            u[i] = (i8)(z - vt1); v[i] = (i8)(z - ut);
+            t1 = (i8)(z - q_); t2 = (i8)(z - q2_);
+            a = (i8)(a - t1); b = (i8)(b - t1); a2 = (i8)(a2 - t2); b2 = (i8)(b2 - t2);
+            d |= a >= 0 ? 0x08 : 0;  d |= b >= 0 ? 0x10 : 0;  d |= a2 >= 0 ? 0x20 : 0;  d |= b2 >= 0 ? 0x40 : 0;
+            x[i] = (i8)(SMAX(a, 0) - qe_); y[i] = (i8)(SMAX(b, 0) - qe_);
+            x2[i] = (i8)(SMAX(a2, 0) - qe2_); y2[i] = (i8)(SMAX(b2, 0) - qe2_);
+            pr[i] = d;
+        }
+    }
+}
+
+int fsvo_force_scalar = 0;   /* tests set this to compare the vectorised rows against the scalar loop */
+
 /* ====================================================================== */
 /* dual-affine: prototype ksw2.h:60-61; body restated (see file header)    */
 int fsvo_extd2(int qlen, const uint8_t* query, int tlen, const uint8_t* target, int8_t m, const int8_t* mat,
@@ -394,7 +466,7 @@ int fsvo_extd2(int qlen, const uint8_t* query, int tlen, const uint8_t* target, 
     int r, t, qe, last_st = -1, last_en = -1, max_sc, min_sc, long_thres, long_diff;
     int approx = !!(flag & FSV_EZ_APPROX_MAX), right = !!(flag & FSV_EZ_RIGHT);
     int32_t H0 = 0, last_H0_t = 0;
-    uint8_t *u, *v, *x, *y, *x2, *y2, *s;
+    uint8_t *u, *v, *x, *y, *x2, *y2, *s, *scr2, *scr3;
     uint8_t q_, q2_, qe_, qe2_, sc_mch, sc_mis, sc_N;
 
     if (dg) memset(dg, 0, sizeof(*dg));
@@ -415,9 +487,11 @@ int fsvo_extd2(int qlen, const uint8_t* query, int tlen, const uint8_t* target, 
     if (q2 + e2 + long_thres * e2 > q + e + long_thres * e) ++long_thres;
     long_diff = long_thres * (e - e2) - (q2 - q) - e2;
 
-    if (wk_setup(&K, qlen, query, tlen, target, w, 7, flag) < 0) { wk_free(&K); return -1; }
+    if (wk_setup(&K, qlen, query, tlen, target, w, 8, flag) < 0) { wk_free(&K); return -1; }
     w = K.w;
     u = K.arr[0]; v = K.arr[1]; x = K.arr[2]; y = K.arr[3]; x2 = K.arr[4]; y2 = K.arr[5]; s = K.arr[6];
+    scr2 = (uint8_t*)wk_alloc(&K, (size_t)K.L + 2 * PAD, 1); scr3 = (uint8_t*)wk_alloc(&K, (size_t)K.L + 2 * PAD, 1);
+    if (!scr2 || !scr3) { wk_free(&K); return -1; }
     memset(u, (uint8_t)(-q - e), (size_t)K.L); memset(v, (uint8_t)(-q - e), (size_t)K.L);
     memset(x, (uint8_t)(-q - e), (size_t)K.L); memset(y, (uint8_t)(-q - e), (size_t)K.L);
     memset(x2, (uint8_t)(-q2 - e2), (size_t)K.L); memset(y2, (uint8_t)(-q2 - e2), (size_t)K.L);
@@ -440,6 +514,11 @@ int fsvo_extd2(int qlen, const uint8_t* query, int tlen, const uint8_t* target, 
         {
             uint8_t* pr = K.with_cigar ? K.p + (size_t)r * K.pitch - st : 0;
             if (K.with_cigar) { K.off[r] = st; K.off_end[r] = en; }
+            if (!dg && !fsvo_force_scalar) {
+                extd2_row_fast(en - st + 1, (i8*)u + st, (i8*)v + st, (i8*)x + st, (i8*)y + st, (i8*)x2 + st, (i8*)y2 + st,
+                               (const i8*)s + st, K.with_cigar ? pr + st : 0, (i8)x1, (i8)x21, (i8)v1, (i8)q_, (i8)q2_, (i8)qe_, (i8)qe2_,
+                               (i8)sc_mch, !K.with_cigar ? 0 : right ? 2 : 1, (i8*)K.arr[7], (i8*)scr2, (i8*)scr3);
+            } else
             for (t = st; t <= en; ++t) {
                 uint8_t z, zc, a, b, a2, b2, ut, tmp, xt1 = x1, x2t1 = x21, vt1 = v1, d = 0;
                 x1 = x[t]; x21 = x2[t]; v1 = v[t];

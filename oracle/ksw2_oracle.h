@@ -23,6 +23,7 @@ int fsvo_extd2(int qlen, const uint8_t* query, int tlen, const uint8_t* target, 
                int8_t q, int8_t e, int8_t q2, int8_t e2, int w, int zdrop, int end_bonus, int flag,
                fsv_result* ez, uint32_t* cigar, int cigar_cap, fsvo_diag* dg);
 int64_t fsvo_task_cells(int qlen, int tlen, int w);
+extern int fsvo_force_scalar;   /* 1 = use the scalar lane loop even without diagnostics */
 int32_t fsvo_gotoh2_global(int qlen, const uint8_t* query, int tlen, const uint8_t* target, int m,
                            const int8_t* mat, int q, int e, int q2, int e2);
 int32_t fsvo_score_cigar(int qlen, const uint8_t* query, int tlen, const uint8_t* target, int m,
