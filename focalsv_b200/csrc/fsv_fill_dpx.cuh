@@ -286,9 +286,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
             }
             // ---- (B) antidiagonal r-1: its maximum, and (only if observable, ksw2.h:164-174) who holds it
             if (r >= 1 && r - 1 < stop_r) {
-                int32_t m = sh_mh[s3m1][0];
-#pragma unroll
-                for (int i = 1; i < NW; ++i) m = max(m, sh_mh[s3m1][i]);
+                const int32_t m = __reduce_max_sync(FULL, lane < NW ? sh_mh[s3m1][lane] : INT32_MIN);
                 M1 = m;
                 const int32_t mr = max(maxrun, M2);      // ez.max once r-2 is accounted for
                 nt1 = m > mr || (T.zdrop >= 0 && mr - m > T.zdrop);
