@@ -155,7 +155,7 @@ def reference_arm(args, rank, world):
         return
     group, n_regions = build_shard(0, 1, args.regions)
     cores = os.cpu_count() or 1
-    idx = cpu_sample(group, args.cpu_seconds, cores, 0.12)
+    idx = cpu_sample(group, args.cpu_seconds, cores, 0.45)
     regions = len(set(group.region_of[idx].tolist()))
     for _ in range(max(args.warmup, 0)):
         run_cpu(group, idx[: max(1, len(idx) // 8)], cores)
@@ -322,7 +322,7 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        idx = cpu_sample(group, args.cpu_seconds, cores, 0.12)
+        idx = cpu_sample(group, args.cpu_seconds, cores, 0.45)
         c, dt, knd = run_cpu(group, idx, cores)
         cpu_baseline = {"value": c / dt / 1e9, "unit": "GCUPS", "cores": cores, "kind": knd,
                         "sample": "%d of %d tasks (%.3g cells) of the same workload, one task per thread" % (len(idx), len(group.tasks), c),
