@@ -81,6 +81,19 @@ __device__ __forceinline__ uint32_t lane_bits(int lo, int hi)
 // packed 16x2 mask of word k (lanes k and k+8) from a 16-bit lane mask
 __device__ __forceinline__ uint32_t word_mask(uint32_t bits, int k) { return prmt(bits << (7 - k), 0u, 0x9988u); }
 
+// explicit shared-memory accesses from one base register (the compiler otherwise rebuilds the address of
+// every __shared__ array on every use)
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) { asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
+__device__ __forceinline__ void atom_min_shared(uint32_t a, uint32_t v) { asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
 // resident CTAs per SM the register budget is tuned for
 template <int NW> struct DpxOcc { static constexpr int value = NW == 1 ? 12 : NW == 2 ? 6 : NW == 4 ? 3 : 2; };
 
@@ -182,13 +195,13 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
 {
     constexpr int NT = NW * 32;
     using KC = DpxConst<DUAL>;
-    __shared__ int32_t sh_task;
-    __shared__ uint32_t sh_bx[2][NW], sh_bv[2][NW], sh_bx2[2][NW], sh_bq[2][NW];   // lane 15 of each warp's last vector
-    __shared__ int32_t sh_bh[2][NW];                                   // ... and its H
-    __shared__ int32_t sh_mh[3][NW];                                   // per-warp max H, ring over 3 antidiagonals
-    __shared__ uint32_t sh_key[3];                                     // best tie key of an antidiagonal
-    __shared__ int32_t sh_hen0[3], sh_hst0[3];                         // H[en0], H[st0]
-    __shared__ int32_t sh_stop;                                        // iteration at which warp 0 saw the z-drop
+    // one shared block, addressed from a single base register:
+    //   edge slots [2 parities][NW] x 32 B : {x, v, x2, qw} of lane 15 of each warp's last vector, then its H
+    //   per-warp max H, ring over 3 antidiagonals; tie key / H[en0] / H[st0] rings; stop flag; task index
+    constexpr uint32_t OFF_EDGE = 0, OFF_MH = 2 * NW * 32, OFF_KEY = OFF_MH + 3 * NW * 4, OFF_HEN0 = OFF_KEY + 12,
+                       OFF_HST0 = OFF_HEN0 + 12, OFF_STOP = OFF_HST0 + 12, OFF_TASK = OFF_STOP + 4, SH_BYTES = OFF_TASK + 4;
+    __shared__ __align__(16) uint32_t sh_raw[(SH_BYTES + 15) / 16 * 4];
+    const uint32_t sb = (uint32_t)__cvta_generic_to_shared(sh_raw);
     const RunCtx& C = P.C;
     const DevScoring& sc = C.sc;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -200,9 +213,9 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) { sh_task = next_task(C, P.Q, table, pending); sh_stop = INT32_MAX; }
+        if (tid == 0) { sts32(sb + OFF_TASK, (uint32_t)next_task(C, P.Q, table, pending)); sts32(sb + OFF_STOP, (uint32_t)INT32_MAX); }
         __syncthreads();
-        const int ti = sh_task;
+        const int ti = (int)lds32(sb + OFF_TASK);
         if (ti < 0) return;
         const DevTask T = C.tasks[ti];
         if (tid == 0 && C.timeline) C.timeline[2 * T.orig] = global_ns();
@@ -249,12 +262,13 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                 if (lane == 0) { nbX = a; nbV = b; nbX2 = c2; nbQ = q2; }
             } else if (lane == 0 && r > 0) {
                 const int pw = (warp + NW - 1) % NW;
-                nbX = sh_bx[ppar][pw]; nbV = sh_bv[ppar][pw]; nbX2 = sh_bx2[ppar][pw]; nbQ = sh_bq[ppar][pw];
+                const uint4 e = lds128(sb + OFF_EDGE + (uint32_t)(ppar * NW + pw) * 32u);
+                nbX = e.x; nbV = e.y; nbX2 = e.z; nbQ = e.w;
             }
 
             // ---- (A) antidiagonal d = r-2 is final: bookkeeping (ksw2_extz2_sse.c:262-269)
             if (r >= 2) {
-                if (sh_stop < r) { dropped = true; break; }      // set during an EARLIER iteration: every thread agrees
+                if ((int)lds32(sb + OFF_STOP) < r) { dropped = true; break; }      // set during an EARLIER iteration: every thread agrees
                 maxrun = max(maxrun, M2);
                 const int d = r - 2;
                 if (warp == 0 && !dropped) {
@@ -263,30 +277,30 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                     cells += en0d - st0d + 1;
                     int max_t = en0d;
                     if (nt2) {
-                        const uint32_t bk = sh_key[s3m2];
+                        const uint32_t bk = lds32(sb + OFF_KEY + 4u * s3m2);
                         if (bk != 0) max_t = (int)((bk - 1u) & ((1u << 26) - 1u));
                     }
                     int32_t h_last = FSV_NEG_INF;
                     if (en0d == tlen - 1) {
-                        h_last = sh_hen0[s3m2];
+                        h_last = (int32_t)lds32(sb + OFF_HEN0 + 4u * s3m2);
                         if (h_last > ez.mte) { ez.mte = h_last; ez.mte_q = d - round_en(en0d); }   // rounded en (:263-264)
                     }
                     if (d - st0d == qlen - 1) {
-                        const int32_t h = sh_hst0[s3m2];
+                        const int32_t h = (int32_t)lds32(sb + OFF_HST0 + 4u * s3m2);
                         if (h > ez.mqe) { ez.mqe = h; ez.mqe_t = st0d; }
                     }
-                    if (ez.apply_zdrop(M2, d, max_t, T.zdrop, sc.e_drop)) { dropped = true; if (lane == 0) sh_stop = r; }
+                    if (ez.apply_zdrop(M2, d, max_t, T.zdrop, sc.e_drop)) { dropped = true; if (lane == 0) sts32(sb + OFF_STOP, (uint32_t)r); }
                     else if (d == n_diag - 1 && en0d == tlen - 1) ez.score = h_last;            // H[tlen-1]
                 }
                 if (d == stop_r - 1) {     // every computed antidiagonal is final
                     if (NW > 1) __syncthreads(); else __syncwarp();
-                    if (sh_stop <= r) dropped = true;
+                    if ((int)lds32(sb + OFF_STOP) <= r) dropped = true;
                     break;
                 }
             }
             // ---- (B) antidiagonal r-1: its maximum, and (only if observable, ksw2.h:164-174) who holds it
             if (r >= 1 && r - 1 < stop_r) {
-                const int32_t m = __reduce_max_sync(FULL, lane < NW ? sh_mh[s3m1][lane] : INT32_MIN);
+                const int32_t m = __reduce_max_sync(FULL, lane < NW ? (int32_t)lds32(sb + OFF_MH + 4u * (uint32_t)(s3m1 * NW + lane)) : INT32_MIN);
                 M1 = m;
                 const int32_t mr = max(maxrun, M2);      // ez.max once r-2 is accounted for
                 nt1 = m > mr || (T.zdrop >= 0 && mr - m > T.zdrop);
@@ -314,10 +328,10 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                         }
                         if (!body && tail) key = 1u + (4u << 26) + (uint32_t)(base + __ffs(tail) - 1);
                     }
-                    atomicMin(&sh_key[s3m1], key);
+                    atom_min_shared(sb + OFF_KEY + 4u * s3m1, key);
                 }
             }
-            if (tid == 0) sh_key[s3] = 0xffffffffu;
+            if (tid == 0) sts32(sb + OFF_KEY + 4u * s3, 0xffffffffu);
 
             // ---- (C) compute antidiagonal r
             int st0 = 0, en0 = -1;
@@ -361,7 +375,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                     // ---- general path: band edges, first row, profile overhang, idle and re-arming vectors
                     int32_t nbH = __shfl_up_sync(FULL, Hb + sext16(Hr[7] >> 16), 1);
                     if (NW == 1) { int32_t h = __shfl_sync(FULL, Hb + sext16(Hr[7] >> 16), 31); if (lane == 0) nbH = h; }
-                    else if (lane == 0 && r > 0) nbH = sh_bh[ppar][(warp + NW - 1) % NW];
+                    else if (lane == 0 && r > 0) nbH = (int32_t)lds32(sb + OFF_EDGE + (uint32_t)(ppar * NW + (warp + NW - 1) % NW) * 32u + 16u);
                     bool rearmed = false;
                     if (Vt < st_) {            // a vector that fell below the band re-arms NT vectors to the right
                         Vt += NT;
@@ -461,8 +475,8 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                         uint32_t pm = 0x80008000u;
 #pragma unroll
                         for (int k = 0; k < 8; ++k) { const uint32_t lm = word_mask(inb, k); pm = __vmaxs2(pm, (Hr[k] & lm) | (0x80008000u & ~lm)); }
-                        if (hi_edge && en0 == tlen - 1) sh_hen0[s3] = Hb + sext16(get_cell(Hr, en0 - base));
-                        if (lo_edge && r - st0 == qlen - 1) sh_hst0[s3] = Hb + sext16(get_cell(Hr, st0 - base));
+                        if (hi_edge && en0 == tlen - 1) sts32(sb + OFF_HEN0 + 4u * s3, (uint32_t)(Hb + sext16(get_cell(Hr, en0 - base))));
+                        if (lo_edge && r - st0 == qlen - 1) sts32(sb + OFF_HST0 + 4u * s3, (uint32_t)(Hb + sext16(get_cell(Hr, st0 - base))));
                         const int mrel = max(sext16(pm), sext16(pm >> 16));
                         habs = Hb + mrel;
                         if ((r & 31) == 31) {   // keep the relative scores small
@@ -477,11 +491,12 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                 habs_p = habs; st0p = st0; en0p = en0;
                 // lane 15 of every warp's last vector, for the next antidiagonal
                 if (NW > 1 && lane == 31) {
-                    sh_bx[par][warp] = X[7]; sh_bv[par][warp] = V[7]; sh_bx2[par][warp] = DUAL ? X2[7] : 0; sh_bq[par][warp] = qw;
-                    sh_bh[par][warp] = Hb + sext16(Hr[7] >> 16);
+                    const uint32_t ea = sb + OFF_EDGE + (uint32_t)(par * NW + warp) * 32u;
+                    sts128(ea, make_uint4(X[7], V[7], DUAL ? X2[7] : 0u, qw));
+                    sts32(ea + 16u, (uint32_t)(Hb + sext16(Hr[7] >> 16)));
                 }
                 const int32_t wmax = __reduce_max_sync(FULL, habs);
-                if (lane == 0) sh_mh[s3][warp] = wmax;
+                if (lane == 0) sts32(sb + OFF_MH + 4u * (uint32_t)(s3 * NW + warp), (uint32_t)wmax);
                 last_st = st; last_en = en;
                 if (TB && ++tb_rip == T.rows_per_page) { tb_rip = 0; ++tb_pg; if (tb_pg < T.tb_pages) tb_page = C.pool.base + (int64_t)table[tb_pg] * C.pool.page_bytes; }
             }
