@@ -142,7 +142,9 @@ __device__ __forceinline__ void dpx_cells(uint32_t (&U)[8], uint32_t (&V)[8], ui
 {
     using C = DpxConst<DUAL>;
     const uint32_t fE = both(C::cE), fF = both(C::cF), fE2 = both(C::cE2), fF2 = both(C::cF2);      // max(.,0) floors
-    const uint32_t oE = both(0x0100u | C::cE), oF = both(0x0100u | C::cF), oE2 = both(0x0100u | C::cE2), oF2 = both(0x0100u | C::cF2);
+    // min(x, code | bit) is `code` when x's value byte is 0 and `code | bit` otherwise: the continuation bit of
+    // ksw2.h:116-118 lands at its final position (0x08 E, 0x10 F, 0x20 E~, 0x40 F~) with one VIMNMX each
+    const uint32_t oE = both(0x08u | C::cE), oF = both(0x10u | C::cF), oE2 = both(0x20u | C::cE2), oF2 = both(0x40u | C::cF2);
     uint32_t tbw[8];
 #pragma unroll
     for (int k = 7; k >= 0; --k) {
@@ -173,12 +175,12 @@ __device__ __forceinline__ void dpx_cells(uint32_t (&U)[8], uint32_t (&V)[8], ui
             const uint32_t xa2 = __viaddmax_s16x2(a2, n2, fE2), ya2 = __viaddmax_s16x2(b2, n2, fF2);
             X[k] = __vsub2(xa, K.kQE); Y[k] = __vsub2(ya, K.kQE);
             X2[k] = __vsub2(xa2, K.kQE2); Y2[k] = __vsub2(ya2, K.kQE2);
-            if (TB) fl = __vmins2(xa, oE) + 2u * __vmins2(ya, oF) + 4u * __vmins2(xa2, oE2) + 8u * __vmins2(ya2, oF2);
+            if (TB) fl = __vmins2(xa, oE) + __vmins2(ya, oF) + __vmins2(xa2, oE2) + __vmins2(ya2, oF2);
         } else {
             X[k] = xa; Y[k] = ya;
-            if (TB) fl = __vmins2(xa, oE) + 2u * __vmins2(ya, oF);
+            if (TB) fl = __vmins2(xa, oE) + __vmins2(ya, oF);
         }
-        if (TB) tbw[k] = ((fl >> 5) & 0x00780078u) | code;
+        if (TB) tbw[k] = (fl & 0x00780078u) | code;      // the low 3 bits of fl hold the sum of the codes (< 8)
     }
     if (TB) {   // 16 traceback bytes in lane order (:195)
         const uint32_t a01 = prmt(tbw[0], tbw[1], 0x6240u), a23 = prmt(tbw[2], tbw[3], 0x6240u);
