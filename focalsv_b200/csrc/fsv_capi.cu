@@ -387,7 +387,8 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
             const int ti = ord[k];
             const DevTask& d = b->tasks[ti];
             if (!b->is_dpx[ti] || d.nw < 6) continue;
-            if ((double)(d.qlen + d.tlen) * t_shared > 0.7 * t_est) { is_excl[ti] = 1; ++n_excl; }
+            const double nd = (double)(d.qlen + d.tlen);
+            if (nd * t_shared > 0.7 * t_est && nd * t_solo > 0.25) { is_excl[ti] = 1; ++n_excl; }   // only tasks that run for >= 0.25 s
         }
     }
     int64_t ws_need = 0, table_off = 0;

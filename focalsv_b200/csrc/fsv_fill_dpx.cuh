@@ -541,7 +541,7 @@ inline bool dpx_supports(const DevScoring& sc, const DevTask& t, bool has_wild)
     return dpx_class_of(dpx_warps_needed(t)) != 0;
 }
 
-constexpr int DPX_EXCL_SMEM = 227 * 1024 - 512;   // dynamic shared memory reserved by an exclusive CTA: nothing else fits on its SM
+constexpr int DPX_EXCL_SMEM = 226 * 1024;   // dynamic shared memory reserved by an exclusive CTA: nothing else fits on its SM
 
 // CTAs to launch for n_tasks tasks of the NW-warp class (persistent CTAs)
 template <bool DUAL, bool TB, int NW>

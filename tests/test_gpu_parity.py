@@ -211,3 +211,51 @@ def test_full_size_properties_cfg2_slice(oracle, aligner):
         assert s == int(res[i]["score"]), (i, s, int(res[i]["score"]))
         assert int(res[i]["cells"]) == api.task_cells(int(t["qlen"]), int(t["tlen"]), int(t["w"]))
     assert n_ok >= len(g.tasks) // 2
+
+
+def test_small_pages_and_tight_pool(oracle):
+    """Traceback paging: 64 KB pages (every task spans many pages) and a pool that only fits a few tasks at a
+    time (CTAs must wait for pages and take small tasks meanwhile) give the same bits."""
+    from focalsv_b200 import api
+    al = api.Aligner(0)
+    try:
+        al.set_option("traceback_page_bytes", 65536)
+        al.set_option("traceback_budget_bytes", 120 * 65536)
+        rng = np.random.default_rng(123)
+        pairs = []
+        for L in list(rng.integers(200, 3000, 60)) + [6000, 7000]:
+            ref = synth.random_seq(rng, int(L))
+            pairs.append((synth.mutate(rng, ref, 0.01, 0.005, 0.005), ref))
+        for preset, w in (("asm5", 301), ("hifiasm", 100)):
+            from focalsv_b200.presets import PRESETS
+            g = synth._pack("paged." + preset, preset, pairs, w, PRESETS[preset].zdrop)
+            bad, ores, gres = compare_group(oracle, al, g)
+            assert not bad, (preset, bad[:5])
+        # a task whose traceback cannot fit the pool at all is refused, not hung
+        ref = synth.random_seq(rng, 40000)
+        g = synth._pack("toolarge", "asm5", [(ref.copy(), ref)], 3001, 200)
+        with pytest.raises(FsvError) as ei:
+            al.align_batch(g.scoring, g.qarena, g.tarena, g.tasks)
+        assert ei.value.code == _abi.ERR_NOMEM
+    finally:
+        al.close()
+
+
+def test_mixed_kernel_variants_share_the_pool(oracle, aligner):
+    """One batch whose tasks land on several kernel variants at once (1/2/4-warp DPX classes, score-only and
+    CIGAR, and wildcard tasks on the general kernel), all running concurrently on one page pool."""
+    rng = np.random.default_rng(321)
+    pairs, flags = [], []
+    for i in range(48):
+        L = int(rng.choice([300, 900, 2500, 5000]))
+        ref = synth.random_seq(rng, L)
+        q = synth.mutate(rng, ref, 0.01, 0.004, 0.004)
+        if i % 7 == 0:
+            q = q.copy(); q[:: 50] = 4          # wildcard bases -> general kernel
+        pairs.append((q, ref)); flags.append([0, _abi.EZ_SCORE_ONLY, _abi.EZ_EXTZ_ONLY, _abi.EZ_RIGHT][i % 4])
+    g = synth._pack("mixed", "map-ont", pairs, -1, 400, flags=np.array(flags, dtype=np.int32))
+    tasks = g.tasks.copy()
+    tasks["w"] = np.where(np.arange(len(tasks)) % 3 == 0, 200, np.where(np.arange(len(tasks)) % 3 == 1, 900, 1800))
+    g = g._replace(tasks=tasks)
+    bad, ores, gres = compare_group(oracle, aligner, g)
+    assert not bad, bad[:5]
