@@ -14,7 +14,7 @@ from . import _abi
 from ._abi import RESULT_DTYPE, TASK_DTYPE, Scoring, Stats
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfocalsv_cuda.so")
+LIB_PATH = os.environ.get("FSV_LIB_PATH") or os.path.join(_HERE, "libfocalsv_cuda.so")   # FSV_LIB_PATH: kernel experiments
 
 # every symbol include/focalsv_cuda.h declares
 EXPORTS = ("fsv_init", "fsv_destroy", "fsv_strerror", "fsv_last_error", "fsv_abi_version", "fsv_device_count",

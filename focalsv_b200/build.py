@@ -46,5 +46,19 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_variant(out, defs):
+    """Experiment builds: same sources with extra -D flags into another file (scripts/ only)."""
+    cmd = [NVCC] + FLAGS + list(defs) + ["-o", out, os.path.join(CSRC, "fsv_capi.cu")]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("nvcc failed")
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose=True))

@@ -35,6 +35,7 @@ struct fsv_ctx {
     // options
     int64_t tb_budget = 0;      // bytes of the traceback page pool (0 = auto: 70% of free memory, at most what the batch needs)
     int force_exact = 0;        // route every task to the general int8-exact kernel
+    int force_excl = 0;         // experiment: every >= 6-warp DPX task on the exclusive (one CTA per SM) launch
     int exact_smem_lanes = 4096;
     int64_t page_bytes = 32ll << 20;
     // scratch shared by the batches of this context (one batch runs at a time)
@@ -165,6 +166,7 @@ extern "C" int fsv_set_option(fsv_ctx* c, const char* key, int64_t value)
     if (!c || !key) return FSV_ERR_INVALID;
     if (!strcmp(key, "traceback_budget_bytes")) { c->tb_budget = value; return FSV_OK; }
     if (!strcmp(key, "force_exact")) { c->force_exact = (int)value; return FSV_OK; }
+    if (!strcmp(key, "force_excl")) { c->force_excl = (int)value; return FSV_OK; }
     if (!strcmp(key, "traceback_page_bytes")) {
         if (value < (1 << 16) || (value & 255)) return FSV_ERR_INVALID;
         c->page_bytes = value; return FSV_OK;
@@ -383,10 +385,11 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
         }
         const double t_est = std::max(cells_sum / dev_cups, longest);
         int n_excl = 0;
-        for (size_t k = 0; k < n && n_excl < c->sm_count / 4; ++k) {
+        for (size_t k = 0; k < n && (n_excl < c->sm_count / 4 || c->force_excl); ++k) {
             const int ti = ord[k];
             const DevTask& d = b->tasks[ti];
             if (!b->is_dpx[ti] || d.nw < 6) continue;
+            if (c->force_excl) { is_excl[ti] = 1; ++n_excl; continue; }
             const double nd = (double)(d.qlen + d.tlen);
             if (nd * t_shared > 0.7 * t_est && nd * t_solo > 0.25) { is_excl[ti] = 1; ++n_excl; }   // only tasks that run for >= 0.25 s
         }
@@ -404,7 +407,7 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
         }
         L.count = (int)b->work.size() - L.begin;
         if (!L.count) return;
-        L.grid = kind == 0 ? exact_grid(c, b->dual, L.count) : excl ? L.count : dpx_grid(c->sm_count, b->dual, with_tb != 0, nw, L.count);
+        L.grid = kind == 0 ? exact_grid(c, b->dual, L.count) : excl ? std::min(L.count, c->sm_count) : dpx_grid(c->sm_count, b->dual, with_tb != 0, nw, L.count);
         L.table_off = table_off;
         table_off += (int64_t)L.grid * b->max_pages_per_task;
         b->launches.push_back(L);

@@ -235,6 +235,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
         int32_t Hb = 0;
         int Vt = tid - NT;          // forces the (re)arm path on the first antidiagonal
         uint32_t tw = 0, qw = 0;
+        uint32_t qpre = 0; int qpre_r = -1;     // query base the lowest vector of the band needs at antidiagonal qpre_r
         EzState ez; ez.reset();     // complete only in warp 0 (the bookkeeping warp)
         int64_t cells = 0;
         int last_st = -1, last_en = -1;
@@ -396,19 +397,27 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                             qw |= (qbse & 3u) << (2 * c);
                         }
                     }
+                    // Everything below is straight-line code (selects and lane masks instead of branches), so
+                    // that the band-edge work of one or two threads is scheduled in between the cell updates
+                    // of the whole warp instead of being serialised behind them; only what happens once per
+                    // vector (re-arming above), once per task (first rows) or never (a negative carry) branches.
                     const int base = Vt << 4;
                     const bool active = Vt >= st_ && Vt <= en_;
                     const bool lo_edge = Vt == st_, hi_edge = Vt == en_;
-                    if (!rearmed) {            // lane c now faces query[r - base - c]
-                        uint32_t q0 = nbQ >> 30;
-                        if (lo_edge) { const int j = r - base; q0 = (j >= 0 && j < qlen) ? (uint32_t)(query[j] & 3u) : 0u; }
-                        qw = (qw << 2) | q0;
+                    {   // lane c now faces query[r - base - c]; the lowest vector of the band reads its new base
+                        // from memory, one antidiagonal ahead (qpre) so that the load is off the critical path
+                        if (lo_edge && !rearmed && qpre_r != r) { const int j = r - base; qpre = (j >= 0 && j < qlen) ? (uint32_t)(query[j] & 3u) : 0u; }
+                        const uint32_t q0 = lo_edge ? qpre : (nbQ >> 30);
+                        qw = rearmed ? qw : ((qw << 2) | q0);
+                        int st0n, en0n;
+                        band_limits(r + 1, qlen, tlen, w, st0n, en0n);
+                        if (Vt == (st0n >> 4)) { const int j = r + 1 - base; qpre = (j >= 0 && j < qlen) ? (uint32_t)(query[j] & 3u) : 0u; qpre_r = r + 1; }
                     }
-                    const int store_end = st0 + ((en0 - st0) >> 4) * 16 + 15;      // profile stores (:126-140)
-                    if (Vt >= st_ && base <= store_end) {
+                    {   // profile stores (:126-140): whole 16-lane stores from st0, so the last one overhangs en0
+                        const int store_end = st0 + ((en0 - st0) >> 4) * 16 + 15;
                         uint32_t sv[8];
                         dpx_profile<DUAL>(sv, tw, qw, K);
-                        const uint32_t bits = lane_bits(st0 - base, store_end - base);
+                        const uint32_t bits = lane_bits(min(st0 - base, 16), store_end - base);      // 0 below st_ and above the overhang
 #pragma unroll
                         for (int k = 0; k < 8; ++k) { const uint32_t lm = word_mask(bits, k); S[k] = (sv[k] & lm) | (S[k] & ~lm); }
                     }
@@ -416,36 +425,37 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                         // operands of word 0: lane -1 is the neighbour's lane 15, lane 7 is our own word 7
                         uint32_t XT0 = prmt(nbX, X[7], 0x5432u), VT0 = prmt(nbV, V[7], 0x5432u);
                         uint32_t X2T0 = DUAL ? prmt(nbX2, X2[7], 0x5432u) : 0;
-                        int32_t fix_prev = 0;      // H of lane en0-1 before this antidiagonal (for :231)
-                        const int ce = en0 - base; // lane of en0 inside this vector (valid when hi_edge)
-                        if (lo_edge) {                                              // carries (:118-122)
-                            uint32_t x1, v1, x21;
-                            if (st > 0) {
-                                if (st - 1 >= last_st && st - 1 <= last_en) { x1 = XT0 & 0xffffu; v1 = VT0 & 0xffffu; x21 = X2T0 & 0xffffu; }
-                                else { x1 = K.gX & 0xffffu; v1 = K.gU & 0xffffu; x21 = K.gX2 & 0xffffu; }
-                            } else {
-                                x1 = K.gX & 0xffffu; x21 = K.gX2 & 0xffffu;
-                                if (DUAL) v1 = hi8(r == 0 ? -K.qe : r < sc.long_thres ? -sc.e : r == sc.long_thres ? sc.long_diff : -sc.e2);
-                                else v1 = hi8(r ? sc.q : 0);
-                            }
-                            XT0 = (XT0 & 0xffff0000u) | x1; VT0 = (VT0 & 0xffff0000u) | v1; X2T0 = (X2T0 & 0xffff0000u) | x21;
-                            if (!DUAL) {   // _mm_cvtsi32_si128(int8_t) sign-extends a negative carry into lanes 1..3 (:146-147)
+                        const int ce = en0 - base; // lane of en0 inside this vector (meaningful when hi_edge)
+                        {   // carries of the lowest vector (:118-122)
+                            const bool inl = st > 0 && st - 1 >= last_st && st - 1 <= last_en;
+                            uint32_t vfirst;       // first column: v1 of an antidiagonal that starts at t = 0
+                            if (DUAL) vfirst = hi8(r == 0 ? -K.qe : r < sc.long_thres ? -sc.e : r == sc.long_thres ? sc.long_diff : -sc.e2);
+                            else vfirst = hi8(r ? sc.q : 0);
+                            const uint32_t x1 = inl ? (XT0 & 0xffffu) : (K.gX & 0xffffu);
+                            const uint32_t v1 = inl ? (VT0 & 0xffffu) : st > 0 ? (K.gU & 0xffffu) : vfirst;
+                            const uint32_t x21 = inl ? (X2T0 & 0xffffu) : (K.gX2 & 0xffffu);
+                            XT0 = lo_edge ? ((XT0 & 0xffff0000u) | x1) : XT0;
+                            VT0 = lo_edge ? ((VT0 & 0xffff0000u) | v1) : VT0;
+                            X2T0 = lo_edge ? ((X2T0 & 0xffff0000u) | x21) : X2T0;
+                            if (!DUAL && lo_edge && ((x1 | v1) & 0x8000u)) {   // _mm_cvtsi32_si128(int8_t) sign-extends a negative carry into lanes 1..3 (:146-147)
                                 if (x1 & 0x8000u) { X[0] = (X[0] & 0xffff0000u) | 0xff00u | KC::cE; X[1] = (X[1] & 0xffff0000u) | 0xff00u | KC::cE; X[2] = (X[2] & 0xffff0000u) | 0xff00u | KC::cE; }
                                 if (v1 & 0x8000u) { V[0] = (V[0] & 0xffff0000u) | 0xff00u; V[1] = (V[1] & 0xffff0000u) | 0xff00u; V[2] = (V[2] & 0xffff0000u) | 0xff00u; }
                             }
                         }
-                        if (en >= r && (r >> 4) == Vt) {                            // first row (:123)
-                            uint32_t eu;
-                            if (DUAL) eu = hi8(r == 0 ? -K.qe : r < sc.long_thres ? -sc.e : r == sc.long_thres ? sc.long_diff : -sc.e2);
-                            else eu = hi8(r ? sc.q : 0);
-                            set_cell(U, r & 15, eu); set_cell(Y, r & 15, K.gY & 0xffffu);
-                            if (DUAL) set_cell(Y2, r & 15, K.gY2 & 0xffffu);
+                        if (en >= r) {             // first row (:123): only while r <= w
+                            if ((r >> 4) == Vt) {
+                                uint32_t eu;
+                                if (DUAL) eu = hi8(r == 0 ? -K.qe : r < sc.long_thres ? -sc.e : r == sc.long_thres ? sc.long_diff : -sc.e2);
+                                else eu = hi8(r ? sc.q : 0);
+                                set_cell(U, r & 15, eu); set_cell(Y, r & 15, K.gY & 0xffffu);
+                                if (DUAL) set_cell(Y2, r & 15, K.gY2 & 0xffffu);
+                            }
                         }
                         // H[en0-1] as the reference's H[] holds it (:231): the value of the previous antidiagonal
                         // while that lane was inside the band, else the value it had when it left the band
-                        if (hi_edge && r > 0 && en0 > 0) {
-                            if (en0 - 1 >= st0p) hprev_keep = ce > 0 ? Hb + sext16(get_cell(Hr, ce - 1)) : nbH;
-                            fix_prev = hprev_keep;
+                        {
+                            const int32_t hleft = ce > 0 ? Hb + sext16(get_cell(Hr, (ce - 1) & 15)) : nbH;
+                            hprev_keep = (hi_edge && r > 0 && en0 > 0 && en0 - 1 >= st0p) ? hleft : hprev_keep;
                         }
 
                         uint4 o;
@@ -453,15 +463,12 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                         if (TB) *reinterpret_cast<uint4*>(tb_page + (int64_t)tb_rip * T.pitch + (base - st)) = o;
 
                         // exact max bookkeeping (:224-260): H[t] += v[t] - qe ; H[en0] from its left neighbour
-                        int32_t fixv = 0;
                         const bool fix = hi_edge && (r == 0 || en0 > 0);
-                        if (fix) {
-                            if (r == 0) fixv = (DUAL ? (int)(int8_t)(V[0] >> 8) : (int)((V[0] >> 8) & 0xffu)) - K.r0_bias;      // H[0] (:262)
-                            else {
-                                const uint32_t u16 = get_cell(U, ce);
-                                const int un = DUAL ? (int)(int8_t)(u16 >> 8) : (int)((u16 >> 8) & 0xffu);
-                                fixv = fix_prev + un - K.bias;          // absolute
-                            }
+                        int32_t fixv;
+                        {
+                            const uint32_t u16 = r == 0 ? (V[0] & 0xffffu) : get_cell(U, ce & 15);        // r == 0: H[0] from v[0] (:262)
+                            const int un = DUAL ? (int)(int8_t)(u16 >> 8) : (int)((u16 >> 8) & 0xffu);
+                            fixv = (r == 0 ? -K.r0_bias : hprev_keep - K.bias) + un;                      // absolute
                         }
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
@@ -469,9 +476,13 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                             if (!DUAL) dv = __vsub2(dv, K.kBias);
                             Hr[k] = __vadd2(Hr[k], dv);
                         }
-                        if (fix) {
-                            if (r == 0 || ce == 0) { Hb = fixv; Hr[0] = Hr[0] & 0xffff0000u; }
-                            else set_cell(Hr, ce, (uint32_t)(fixv - Hb) & 0xffffu);
+                        {   // lane en0 takes the value derived from its left neighbour; a vector whose lane 0 is en0
+                            // (or the very first cell) restarts its base there
+                            Hb = (fix && (r == 0 || ce == 0)) ? fixv : Hb;
+                            const uint32_t fv = both((uint32_t)(fixv - Hb) & 0xffffu);
+                            const uint32_t fbit = fix ? (1u << (ce & 15)) : 0u;
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) { const uint32_t lm = word_mask(fbit, k); Hr[k] = (fv & lm) | (Hr[k] & ~lm); }
                         }
                         const uint32_t inb = lane_bits(st0 - base, en0 - base);
                         uint32_t pm = 0x80008000u;

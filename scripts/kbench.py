@@ -9,15 +9,17 @@ w = int(sys.argv[3]) if len(sys.argv)>3 else 3001
 n = int(sys.argv[4]) if len(sys.argv)>4 else 600
 flag = int(sys.argv[5],0) if len(sys.argv)>5 else 0
 force = int(sys.argv[6]) if len(sys.argv)>6 else 0
+opts = [a.split("=") for a in sys.argv[7:]]      # extra fsv_set_option pairs, e.g. force_excl=1
 rng = np.random.default_rng(5)
 pairs=[]
 for i in range(n):
     ref = synth.random_seq(rng, L)
     q,_ = synth.plant_svs(rng, ref, 2, max_net=min(w//2-50, 1200), max_len=min(w//2-60, 1000))
     pairs.append((synth.mutate(rng,q,0.0006,0.0002,0.0002), ref))
-g = synth._pack("k", preset, pairs, w, PRESETS[preset].zdrop, flag=flag)
+g = synth._pack("k", preset, pairs, w, int(__import__("os").environ.get("KB_ZDROP", PRESETS[preset].zdrop)), flag=flag)
 al = api.Aligner(0)
 if force: al.set_option("force_exact",1)
+for k, v in opts: al.set_option(k, int(v))
 b = al.batch(g.scoring, g.qarena, g.tarena, g.tasks)
 b.run()
 for rep in range(3):
