@@ -38,11 +38,15 @@ struct fsv_ctx {
     int force_excl = 0;         // experiment: every >= 6-warp DPX task on the exclusive (one CTA per SM) launch
     int exact_smem_lanes = 4096;
     int64_t page_bytes = 32ll << 20;
+    int lazy_min_pages = 16;    // DPX tasks with at least this many traceback pages take them as they advance (0 = all up front)
+    int pool_stall_ms = 60000;  // lazy-pool watchdog
+    int lazy_fill_pct = 65;     // admission of such a task waits while the projected peak of those running exceeds this share of the pool
     // scratch shared by the batches of this context (one batch runs at a time)
     uint8_t* d_pool = nullptr; size_t pool_cap = 0;
     uint8_t* d_ws = nullptr; size_t ws_cap = 0;
     int32_t* d_tables = nullptr; size_t tables_cap = 0;
     int32_t* d_free_stack = nullptr; size_t stack_cap = 0;
+    int32_t* d_lazy = nullptr; size_t lazy_cap = 0;      // LazyState followed by the per-CTA slot index
 };
 
 // one fill-kernel launch: a slice of the work list, largest task first
@@ -71,8 +75,10 @@ struct fsv_batch {
     int64_t cigar_cap_words = 0;
     int64_t ws_lanes = 0;
     int64_t pool_pages = 0;           // pages of the traceback pool this batch wants
+    int64_t pages_total = 0;          // pages all its tasks need together
     int32_t max_pages_per_task = 1;
     int64_t tb_bytes_total = 0;       // traceback bytes a full run writes
+    int64_t max_rows = 1;             // antidiagonals of the longest task that stores traceback
     // device
     uint8_t *d_q = nullptr, *d_t = nullptr;
     DevTask* d_tasks = nullptr;
@@ -149,6 +155,7 @@ extern "C" void fsv_destroy(fsv_ctx* c)
     if (c->d_ws) cudaFree(c->d_ws);
     if (c->d_tables) cudaFree(c->d_tables);
     if (c->d_free_stack) cudaFree(c->d_free_stack);
+    if (c->d_lazy) cudaFree(c->d_lazy);
     for (auto ks : c->kstream) if (ks) cudaStreamDestroy(ks);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -167,6 +174,15 @@ extern "C" int fsv_set_option(fsv_ctx* c, const char* key, int64_t value)
     if (!strcmp(key, "traceback_budget_bytes")) { c->tb_budget = value; return FSV_OK; }
     if (!strcmp(key, "force_exact")) { c->force_exact = (int)value; return FSV_OK; }
     if (!strcmp(key, "force_excl")) { c->force_excl = (int)value; return FSV_OK; }
+    if (!strcmp(key, "lazy_min_pages")) {      // 0 = off; a lazy task starts with two pages, so at least 3
+        if (value < 0 || value > (1 << 20)) return FSV_ERR_INVALID;
+        c->lazy_min_pages = value == 0 ? 0 : (int)std::max<int64_t>(value, 3); return FSV_OK;
+    }
+    if (!strcmp(key, "pool_stall_ms")) { if (value < 100) return FSV_ERR_INVALID; c->pool_stall_ms = (int)value; return FSV_OK; }
+    if (!strcmp(key, "lazy_fill_pct")) {
+        if (value < 1 || value > 100) return FSV_ERR_INVALID;
+        c->lazy_fill_pct = (int)value; return FSV_OK;
+    }
     if (!strcmp(key, "traceback_page_bytes")) {
         if (value < (1 << 16) || (value & 255)) return FSV_ERR_INVALID;
         c->page_bytes = value; return FSV_OK;
@@ -335,6 +351,7 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
             pages_total += d.tb_pages;
             b->max_pages_per_task = std::max(b->max_pages_per_task, d.tb_pages);
             b->tb_bytes_total += rows * d.pitch;
+            b->max_rows = std::max(b->max_rows, rows);
         }
         if (!c->force_exact) {
             // the DPX kernel packs bases in 2 bits: a task with a wildcard base goes to the general kernel
@@ -359,6 +376,7 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
         }
         int64_t cap_pages = std::max<int64_t>(budget / c->page_bytes, 0);
         b->pool_pages = std::min(pages_total, cap_pages);
+        b->pages_total = pages_total;
         if (b->max_pages_per_task > 1 || pages_total > 0)
             if (b->pool_pages < b->max_pages_per_task) {
                 c->last_error = "the traceback of the largest task (" + std::to_string(b->max_pages_per_task) +
@@ -469,8 +487,9 @@ extern "C" int fsv_batch_run(fsv_batch* b)
     fsv_ctx* c = b->ctx;
     CK(c, cudaSetDevice(c->device));
     // ---- scratch: page pool, free stack, page tables, general-kernel windows
-    int64_t tables = 0, ws_bytes = 0;
+    int64_t tables = 0, ws_bytes = 0, n_slots = 0;
     for (auto& L : b->launches) {
+        n_slots += L.grid;
         tables = std::max<int64_t>(tables, L.table_off + (int64_t)L.grid * b->max_pages_per_task);
         if (L.kind == 0 && b->ws_lanes) ws_bytes = (int64_t)L.grid * b->ws_lanes * (EXACT_NARR + 4);
     }
@@ -479,6 +498,10 @@ extern "C" int fsv_batch_run(fsv_batch* b)
     if ((rc = grow(c, &c->d_free_stack, &c->stack_cap, (size_t)(b->pool_pages + 1) * 4)) != FSV_OK) return rc;
     if ((rc = grow(c, &c->d_tables, &c->tables_cap, (size_t)(tables + 1) * 4)) != FSV_OK) return rc;
     if ((rc = grow(c, &c->d_ws, &c->ws_cap, (size_t)ws_bytes)) != FSV_OK) return rc;
+    const size_t lazy_bytes = sizeof(LazyState) + (size_t)(n_slots + 1) * 4;
+    if ((rc = grow(c, &c->d_lazy, &c->lazy_cap, lazy_bytes)) != FSV_OK) return rc;
+    CK(c, cudaMemsetAsync(c->d_lazy, 0, sizeof(LazyState), c->stream));
+    CK(c, cudaMemsetAsync(reinterpret_cast<uint8_t*>(c->d_lazy) + sizeof(LazyState), 0xff, (size_t)(n_slots + 1) * 4, c->stream));
     {   // control block: overflow flag, pool lock, free count, queue states; free stack = every page
         std::vector<int32_t> stack((size_t)b->pool_pages + 1);
         for (int64_t i = 0; i < b->pool_pages; ++i) stack[(size_t)i] = (int32_t)i;
@@ -496,7 +519,15 @@ extern "C" int fsv_batch_run(fsv_batch* b)
     RunCtx R{};
     R.qarena = b->d_q; R.tarena = b->d_t; R.tasks = b->d_tasks; R.results = b->d_results;
     R.pool.base = c->d_pool; R.pool.page_bytes = c->page_bytes; R.pool.n_pages = (int32_t)b->pool_pages;
-    R.pool.free_stack = c->d_free_stack; R.pool.n_free = b->d_ctrl + 2; R.pool.lock = b->d_ctrl + 1;
+    R.pool.free_stack = c->d_free_stack; R.pool.n_free = b->d_ctrl + 2; R.pool.lock = b->d_ctrl + 1; R.pool.progress = b->d_ctrl + 3; R.pool.gate = b->d_ctrl + 4;
+    // lazy growth only pays (and only costs) when the batch's traceback does not fit the pool at once
+    const bool lazy_on = c->lazy_min_pages > 0 && b->pool_pages < b->pages_total;
+    R.pool.lazy = lazy_on ? reinterpret_cast<LazyState*>(c->d_lazy) : nullptr;
+    R.pool.slot_idx = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(c->d_lazy) + sizeof(LazyState));
+    R.pool.lazy_min_pages = lazy_on ? c->lazy_min_pages : 0;
+    R.pool.lazy_fill = (float)c->lazy_fill_pct * 0.01f;
+    R.pool.stall_ms = c->pool_stall_ms;
+    R.pool.bucket_rows = (int32_t)(b->max_rows / LAZY_BUCKETS + 1);
     R.max_pages_per_task = b->max_pages_per_task;
     R.cigar = b->d_cigar; R.cigar_cursor = b->d_cursor; R.cigar_cap = b->cigar_cap_words; R.overflow = b->d_ctrl + 0;
     R.timeline = b->d_timeline;
@@ -508,12 +539,14 @@ extern "C" int fsv_batch_run(fsv_batch* b)
     CK(c, cudaEventRecord(e0, c->stream));
     // every kernel variant runs concurrently on its own stream; they share the page pool, so the long
     // tasks of one class overlap the short tasks of all the others
+    int32_t slot_base = 0;
     for (size_t i = 0; i < b->launches.size(); ++i) {
         const Launch& L = b->launches[i];
         cudaStream_t ks = c->kstream[i] ? c->kstream[i] : c->stream;
         CK(c, cudaStreamWaitEvent(ks, e0, 0));
         TaskQueue Q{reinterpret_cast<unsigned long long*>(b->d_ctrl + 8 + 2 * i), b->d_work + L.begin};
         R.page_tables = c->d_tables + L.table_off;
+        R.slot_base = slot_base; slot_base += L.grid;
         if (L.kind == 1) {
             DpxParams D{R, Q};
             rc = dpx_launch(ks, b->dual, L.with_tb != 0, L.nw, L.grid, L.excl != 0, D, &c->last_error);

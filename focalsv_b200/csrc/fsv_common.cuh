@@ -92,9 +92,28 @@ namespace fsv {
 
 // ---------------------------------------------------------------------------
 // Paged traceback pool.  Traceback rows (one per antidiagonal, `pitch` bytes) of a task live in
-// fixed-size pages taken from one device-wide pool when the task STARTS and given back when its
-// CIGAR has been reconstructed, so the resident traceback is bounded by the tasks in flight
-// (one per CTA), not by the batch.  Row r of a task sits in page r / rows_per_page.
+// fixed-size pages of one device-wide pool and are given back when the task's CIGAR has been
+// reconstructed, so the resident traceback is bounded by the tasks in flight (one per CTA), not by the
+// batch.  Row r of a task sits in page r / rows_per_page.
+//   * short tasks take all their pages when they START ("up front");
+//   * long tasks (>= lazy_min_pages) take theirs ONE BY ONE as their antidiagonals advance ("lazy"): a
+//     task that runs for seconds then holds on average half of its traceback, which is what bounds how
+//     many long tasks can overlap.  Lazy growth could deadlock (every running task waiting for a page), so
+//     every grant — a lazy page, the admission of a lazy task, the pages of a short task — is made only
+//     if the lazy tasks can still all finish one after the other with the pages that remain free
+//     (banker's algorithm, exact: the list of lazy tasks is short and scanned under the pool lock).
+//     Admission of a lazy task additionally projects the growth of the lazy tasks already running
+//     (same antidiagonal rate for all) and waits while the projected peak exceeds `lazy_fill` of the pool,
+//     which staggers the long tasks instead of letting them hit the limit together.
+constexpr int LAZY_MAX = 256;        // lazy tasks in flight (more wait for a slot)
+constexpr int LAZY_BUCKETS = 32;     // time buckets of the growth projection
+struct LazyState {                   // device global memory, touched only under the pool lock
+    int32_t n;                       // lazy tasks in flight
+    int32_t pad_[3];
+    int32_t held[LAZY_MAX], total[LAZY_MAX], rpp[LAZY_MAX], slot[LAZY_MAX];   // pages held / needed, rows per page, CTA slot
+    int32_t done[LAZY_MAX];          // scratch of the safety check
+    float b_held[LAZY_BUCKETS], b_rate[LAZY_BUCKETS];                         // scratch of the projection
+};
 struct TbPool {
     uint8_t* base;          // n_pages * page_bytes
     int64_t page_bytes;
@@ -102,6 +121,14 @@ struct TbPool {
     int32_t* free_stack;    // page ids, free_stack[0 .. *n_free)
     int32_t* n_free;
     int32_t* lock;          // 0 = free
+    int32_t* progress;      // bumped (under the lock) by every grant and every release: the stall watchdog's heartbeat
+    int32_t* gate;          // waiters for memory poll ONE at a time (the checks run under the pool lock)
+    LazyState* lazy;        // null = every task takes its pages up front
+    int32_t* slot_idx;      // per CTA slot: index into lazy->* of the task it runs, or -1
+    int32_t lazy_min_pages; // tasks with at least this many pages grow lazily (<= 0: none)
+    int32_t bucket_rows;    // antidiagonals per projection bucket
+    float lazy_fill;        // projected peak of the lazy tasks must stay below lazy_fill * n_pages
+    int32_t stall_ms;       // watchdog: no grant and no release on the whole device for this long = broken, trap
 };
 
 __device__ __forceinline__ void pool_lock(int32_t* lock)
@@ -115,28 +142,123 @@ __device__ __forceinline__ void pool_unlock(int32_t* lock)
     __threadfence();
     atomicExch(lock, 0);
 }
-// called by ONE thread; returns false when fewer than n pages are free
+
+// Under the pool lock: can every lazy task still finish, one after the other, if `free_after` pages
+// stay free?  Entry `self` (if >= 0) is evaluated as holding `self_held` pages.
+__device__ inline bool lazy_safe(const TbPool& P, int free_after, int self, int self_held)
+{
+    volatile LazyState* L = P.lazy;
+    const int n = L->n;
+    for (int i = 0; i < n; ++i) L->done[i] = 0;
+    int av = free_after, left = n;
+    bool progress = true;
+    while (left > 0 && progress) {
+        progress = false;
+        for (int i = 0; i < n; ++i) {
+            if (L->done[i]) continue;
+            const int h = i == self ? self_held : L->held[i];
+            if (L->total[i] - h <= av) { av += h; L->done[i] = 1; --left; progress = true; }
+        }
+    }
+    return left == 0;
+}
+// Under the pool lock: projected peak (pages) of the lazy tasks if a new one (total pages, rows per page) starts now.
+__device__ inline float lazy_projected_peak(const TbPool& P, int new_total, int new_rpp)
+{
+    volatile LazyState* L = P.lazy;
+    for (int b = 0; b < LAZY_BUCKETS; ++b) { L->b_held[b] = 0.f; L->b_rate[b] = 0.f; }
+    const int n = L->n;
+    for (int i = 0; i <= n; ++i) {
+        const int h = i < n ? L->held[i] : 0, t = i < n ? L->total[i] : new_total, rp = i < n ? L->rpp[i] : new_rpp;
+        int b = (int)(((long long)(t - h) * rp) / P.bucket_rows);       // bucket in which the task ends
+        if (b >= LAZY_BUCKETS) b = LAZY_BUCKETS - 1;
+        L->b_held[b] += (float)h; L->b_rate[b] += 1.0f / (float)rp;
+    }
+    float alive_h = 0.f, alive_r = 0.f, peak = 0.f;
+    for (int b = LAZY_BUCKETS - 1; b >= 0; --b) {                        // tasks of bucket b count as alive until its end
+        alive_h += L->b_held[b]; alive_r += L->b_rate[b];
+        const float u = alive_h + alive_r * (float)(b + 1) * (float)P.bucket_rows;
+        peak = u > peak ? u : peak;
+    }
+    return peak;
+}
+
+// All of these are called by ONE thread of a CTA.
+// Up-front allocation of n pages; false when they are not free or would endanger the lazy tasks.
 __device__ inline bool pool_try_alloc(const TbPool& P, int n, int32_t* table)
 {
     if (n <= 0) return true;
     bool ok = false;
     pool_lock(P.lock);
     int nf = *(volatile int32_t*)P.n_free;
-    if (nf >= n) {
+    if (nf >= n && (!P.lazy || ((volatile LazyState*)P.lazy)->n == 0 || lazy_safe(P, nf - n, -1, 0))) {
         for (int i = 0; i < n; ++i) table[i] = ((volatile int32_t*)P.free_stack)[nf - 1 - i];
         *(volatile int32_t*)P.n_free = nf - n;
+        ++*(volatile int32_t*)P.progress;
         ok = true;
     }
     pool_unlock(P.lock);
     return ok;
 }
-__device__ inline void pool_free(const TbPool& P, int n, const int32_t* table)
+// Admission of a lazy task of `total` pages run by CTA slot `slot`: takes its first min(2, total) pages.
+__device__ inline bool pool_lazy_admit(const TbPool& P, int slot, int total, int rpp, int32_t* table, int& held)
 {
-    if (n <= 0) return;
+    bool ok = false;
+    const int first = total < 2 ? total : 2;
+    pool_lock(P.lock);
+    volatile LazyState* L = P.lazy;
+    const int nf = *(volatile int32_t*)P.n_free, n = L->n;
+    if (nf >= first && n < LAZY_MAX) {
+        bool fits = n == 0 || lazy_projected_peak(P, total, rpp) <= P.lazy_fill * (float)P.n_pages;
+        if (fits) {
+            L->held[n] = first; L->total[n] = total; L->rpp[n] = rpp; L->slot[n] = slot; L->n = n + 1;
+            if (lazy_safe(P, nf - first, -1, 0)) {
+                for (int i = 0; i < first; ++i) table[i] = ((volatile int32_t*)P.free_stack)[nf - 1 - i];
+                *(volatile int32_t*)P.n_free = nf - first;
+                ++*(volatile int32_t*)P.progress;
+                ((volatile int32_t*)P.slot_idx)[slot] = n;
+                held = first; ok = true;
+            } else L->n = n;
+        }
+    }
+    pool_unlock(P.lock);
+    return ok;
+}
+// One more page for the lazy task of CTA slot `slot` (table[held] receives it).
+__device__ inline bool pool_lazy_grab(const TbPool& P, int slot, int32_t* table, int& held)
+{
+    bool ok = false;
+    pool_lock(P.lock);
+    volatile LazyState* L = P.lazy;
+    const int nf = *(volatile int32_t*)P.n_free, me = ((volatile int32_t*)P.slot_idx)[slot];
+    if (nf >= 1 && lazy_safe(P, nf - 1, me, held + 1)) {
+        table[held] = ((volatile int32_t*)P.free_stack)[nf - 1];
+        *(volatile int32_t*)P.n_free = nf - 1;
+        ++*(volatile int32_t*)P.progress;
+        L->held[me] = ++held;
+        ok = true;
+    }
+    pool_unlock(P.lock);
+    return ok;
+}
+// Gives back table[0 .. n); `slot` >= 0 also retires the lazy task of that CTA slot.
+__device__ inline void pool_free(const TbPool& P, int n, const int32_t* table, int slot = -1)
+{
+    if (n <= 0 && slot < 0) return;
     pool_lock(P.lock);
     int nf = *(volatile int32_t*)P.n_free;
     for (int i = 0; i < n; ++i) ((volatile int32_t*)P.free_stack)[nf + i] = table[i];
     *(volatile int32_t*)P.n_free = nf + n;
+    ++*(volatile int32_t*)P.progress;
+    if (slot >= 0) {
+        volatile LazyState* L = P.lazy;
+        const int me = ((volatile int32_t*)P.slot_idx)[slot], last = L->n - 1;
+        if (me != last) {        // keep the list dense
+            L->held[me] = L->held[last]; L->total[me] = L->total[last]; L->rpp[me] = L->rpp[last];
+            const int s2 = L->slot[last]; L->slot[me] = s2; ((volatile int32_t*)P.slot_idx)[s2] = me;
+        }
+        L->n = last; ((volatile int32_t*)P.slot_idx)[slot] = -1;
+    }
     pool_unlock(P.lock);
 }
 
@@ -171,6 +293,7 @@ struct RunCtx {
     fsv_result* results;
     TbPool pool;
     int32_t* page_tables;        // per CTA: max_pages_per_task entries
+    int32_t slot_base;           // pool slot of this launch's CTA 0 (slot = slot_base + blockIdx.x)
     int32_t max_pages_per_task;
     uint32_t* cigar;             // compact CIGAR arena
     unsigned long long* cigar_cursor;
@@ -180,34 +303,83 @@ struct RunCtx {
     DevScoring sc;
 };
 
-// Picks the next task for this CTA (thread 0 only) and gets its traceback pages.
-// `pending` carries a claimed task that is still waiting for memory.  Returns the task index or -1.
-__device__ inline int next_task(const RunCtx& C, const TaskQueue& Q, int32_t* table, int& pending)
-{
-    for (;;) {
-        if (pending >= 0) {
-            if (pool_try_alloc(C.pool, C.tasks[pending].tb_pages, table)) { int t = pending; pending = -1; return t; }
-            int t = queue_take(Q, 1);                       // memory is short: do a small task meanwhile
-            if (t >= 0) {
-                if (pool_try_alloc(C.pool, C.tasks[t].tb_pages, table)) return t;
-                // not even the small one fits right now: wait for running tasks to finish
-                for (;;) { __nanosleep(2000); if (pool_try_alloc(C.pool, C.tasks[t].tb_pages, table)) return t; }
-            }
-            __nanosleep(2000);                              // queue drained: wait for memory
-            continue;
-        }
-        int t = queue_take(Q, 0);
-        if (t < 0) return -1;
-        if (pool_try_alloc(C.pool, C.tasks[t].tb_pages, table)) return t;
-        pending = t;
-    }
-}
-
 __device__ __forceinline__ long long global_ns()
 {
     long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
+}
+
+// Stall watchdog of the lazy pool: a waiter traps (the launch fails, nothing hangs) if NO task on the device
+// got or returned a page for `stall_ms` (a minute by default) — with lazy growth every running task does so many times a second.
+struct StallWatch {
+    long long t0 = 0; int32_t seen = 0;
+    __device__ __forceinline__ void poll(const TbPool& P)
+    {
+        if (!P.lazy) return;
+        const int32_t p = *(volatile int32_t*)P.progress;
+        const long long now = global_ns();
+        if (!t0 || p != seen) { t0 = now; seen = p; }
+        else if (now - t0 > (long long)P.stall_ms * 1000000ll) {
+            volatile LazyState* L = P.lazy;
+            printf("fsv pool stall: block %d free %d lazy %d:", (int)blockIdx.x, *(volatile int32_t*)P.n_free, L->n);
+            for (int i = 0; i < L->n && i < 24; ++i) printf(" [%d/%d s%d]", L->held[i], L->total[i], L->slot[i]);
+            printf("\n");
+            __trap();
+        }
+    }
+};
+
+// Pages for task t (thread 0 only): up front, or lazily (`lazy_ok`, DPX kernels) when it is long.
+// `held` receives the pages taken now; held < tb_pages marks a lazy task.
+__device__ inline bool task_pages(const RunCtx& C, int t, int32_t* table, bool lazy_ok, int& held)
+{
+    const DevTask& T = C.tasks[t];
+    if (lazy_ok && C.pool.lazy && C.pool.lazy_min_pages > 0 && T.tb_pages >= C.pool.lazy_min_pages)
+        return pool_lazy_admit(C.pool, C.slot_base + (int)blockIdx.x, T.tb_pages, T.rows_per_page, table, held);
+    if (!pool_try_alloc(C.pool, T.tb_pages, table)) return false;
+    held = T.tb_pages;
+    return true;
+}
+
+// One attempt of a WAITING CTA: only one waiter at a time runs the (locked, not free) admission checks, the
+// others sleep, so that the tasks that are running never queue behind a crowd of pollers for the pool lock.
+__device__ inline bool task_pages_gated(const RunCtx& C, int t, int32_t* table, bool lazy_ok, int& held)
+{
+    if (atomicCAS(C.pool.gate, 0, 1) != 0) return false;
+    const bool ok = task_pages(C, t, table, lazy_ok, held);
+    __threadfence();
+    atomicExch(C.pool.gate, 0);
+    return ok;
+}
+
+// Picks the next task for this CTA (thread 0 only) and gets its traceback pages.
+// `pending` carries a claimed task that is still waiting for memory.  Returns the task index or -1.
+__device__ inline int next_task(const RunCtx& C, const TaskQueue& Q, int32_t* table, int& pending, bool lazy_ok, int& held)
+{
+    StallWatch watch;
+    for (;;) {
+        if (pending >= 0) {
+            if (task_pages_gated(C, pending, table, lazy_ok, held)) { int t = pending; pending = -1; return t; }
+            int t = queue_take(Q, 1);                       // memory is short: do a small task meanwhile
+            if (t >= 0) {
+                if (task_pages(C, t, table, lazy_ok, held)) return t;
+                // not even the small one fits right now: wait for running tasks to finish
+                for (;;) {
+                    __nanosleep(20000);
+                    if (task_pages_gated(C, t, table, lazy_ok, held)) return t;
+                    watch.poll(C.pool);
+                }
+            }
+            __nanosleep(20000);                             // queue drained: wait for memory
+            watch.poll(C.pool);
+            continue;
+        }
+        int t = queue_take(Q, 0);
+        if (t < 0) return -1;
+        if (task_pages(C, t, table, lazy_ok, held)) return t;
+        pending = t;
+    }
 }
 
 // byte address of traceback row r of a task (rows_per_page = page_bytes / pitch)

@@ -212,14 +212,16 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
     const uint32_t extSel = DUAL ? 0xB391u : 0x4341u;                  // int8 (signed / unsigned) -> int16
     int32_t* table = C.page_tables + (int64_t)blockIdx.x * C.max_pages_per_task;
     int pending = -1;
+    int tb_held = 0;            // thread 0: traceback pages this task holds (fewer than tb_pages: a lazily growing task)
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) { sts32(sb + OFF_TASK, (uint32_t)next_task(C, P.Q, table, pending)); sts32(sb + OFF_STOP, (uint32_t)INT32_MAX); }
+        if (tid == 0) { sts32(sb + OFF_TASK, (uint32_t)next_task(C, P.Q, table, pending, true, tb_held)); sts32(sb + OFF_STOP, (uint32_t)INT32_MAX); }
         __syncthreads();
         const int ti = (int)lds32(sb + OFF_TASK);
         if (ti < 0) return;
         const DevTask T = C.tasks[ti];
+        const bool tb_lazy = tid == 0 && tb_held < T.tb_pages;      // (thread 0) pages are taken as the antidiagonals advance
         if (tid == 0 && C.timeline) C.timeline[2 * T.orig] = global_ns();
         const int qlen = T.qlen, tlen = T.tlen, w = T.w;
         const uint8_t* query = C.qarena + T.q_off;
@@ -511,7 +513,15 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                 const int32_t wmax = __reduce_max_sync(FULL, habs);
                 if (lane == 0) sts32(sb + OFF_MH + 4u * (uint32_t)(s3 * NW + warp), (uint32_t)wmax);
                 last_st = st; last_en = en;
-                if (TB && ++tb_rip == T.rows_per_page) { tb_rip = 0; ++tb_pg; if (tb_pg < T.tb_pages) tb_page = C.pool.base + (int64_t)table[tb_pg] * C.pool.page_bytes; }
+                if (TB && ++tb_rip == T.rows_per_page) {
+                    tb_rip = 0; ++tb_pg;
+                    if (tb_pg < T.tb_pages) tb_page = C.pool.base + (int64_t)table[tb_pg] * C.pool.page_bytes;
+                    if (tb_lazy) {         // one page ahead: the CTA reads table[tb_pg + 1] a whole page of antidiagonals from now
+                        StallWatch watch;
+                        while (tb_held < T.tb_pages && tb_held < tb_pg + 2)
+                            if (!pool_lazy_grab(C.pool, C.slot_base + (int)blockIdx.x, table, tb_held)) { __nanosleep(4000); watch.poll(C.pool); }
+                    }
+                }
             }
             // ---- (D) the one barrier of the antidiagonal
             if (NW > 1) __syncthreads(); else __syncwarp();
@@ -523,7 +533,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
         __syncthreads();             // every traceback row is written
         if (warp == 0) finish_task(C, T, table, ez, cells, TB);
         __syncthreads();
-        if (tid == 0) { pool_free(C.pool, T.tb_pages, table); if (C.timeline) C.timeline[2 * T.orig + 1] = global_ns(); }
+        if (tid == 0) { pool_free(C.pool, tb_held, table, tb_lazy ? C.slot_base + (int)blockIdx.x : -1); if (C.timeline) C.timeline[2 * T.orig + 1] = global_ns(); }
     }
 }
 

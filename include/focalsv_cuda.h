@@ -125,8 +125,14 @@ const char* fsv_last_error(const fsv_ctx* ctx);
 int fsv_abi_version(void);
 int fsv_device_count(void);
 int fsv_get_stats(const fsv_ctx* ctx, fsv_stats* out);
-/* tunables: "traceback_budget_bytes", "force_exact" (1 = int8-exact kernel only),
- * "fill_threads" ... returns FSV_ERR_INVALID for unknown keys */
+/* tunables (FSV_ERR_INVALID for unknown keys or bad values):
+ *   "traceback_budget_bytes"  size of the traceback page pool (0 = auto)
+ *   "traceback_page_bytes"    page size of the pool (default 32 MiB)
+ *   "lazy_min_pages"          tasks with at least this many traceback pages take them as they advance (default 16; 0 = off)
+ *   "lazy_fill_pct"           such a task starts only while the projected peak of those running stays below this share of the pool (default 65)
+ *   "pool_stall_ms"           watchdog of the lazy pool (default 60000)
+ *   "force_exact"             1 = int8-exact general kernel only
+ *   "exact_smem_lanes", "force_excl"   kernel experiments */
 int fsv_set_option(fsv_ctx* ctx, const char* key, int64_t value);
 
 /* ---- one-call batch API (host buffers in, host buffers out) ----------

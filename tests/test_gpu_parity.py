@@ -226,11 +226,16 @@ def test_small_pages_and_tight_pool(oracle):
         for L in list(rng.integers(200, 3000, 60)) + [6000, 7000]:
             ref = synth.random_seq(rng, int(L))
             pairs.append((synth.mutate(rng, ref, 0.01, 0.005, 0.005), ref))
-        for preset, w in (("asm5", 301), ("hifiasm", 100)):
-            from focalsv_b200.presets import PRESETS
-            g = synth._pack("paged." + preset, preset, pairs, w, PRESETS[preset].zdrop)
-            bad, ores, gres = compare_group(oracle, al, g)
-            assert not bad, (preset, bad[:5])
+        from focalsv_b200.presets import PRESETS
+        # lazy_min_pages: 16 = default (the longest tasks take their pages as they advance, the others up front),
+        # 3 = nearly every task grows lazily (banker's check on every grant), 0 = every task up front
+        for lazy in (16, 3, 0):
+            al.set_option("lazy_min_pages", lazy)
+            al.set_option("pool_stall_ms", 5000)
+            for preset, w in (("asm5", 301), ("hifiasm", 100)):
+                g = synth._pack("paged." + preset, preset, pairs, w, PRESETS[preset].zdrop)
+                bad, ores, gres = compare_group(oracle, al, g)
+                assert not bad, (lazy, preset, bad[:5])
         # a task whose traceback cannot fit the pool at all is refused, not hung
         ref = synth.random_seq(rng, 40000)
         g = synth._pack("toolarge", "asm5", [(ref.copy(), ref)], 3001, 200)
