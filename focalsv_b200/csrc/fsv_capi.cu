@@ -10,6 +10,7 @@
 // fsv_fill_exact.cuh / fsv_fill_dpx.cuh / fsv_backtrack.cuh.
 #include <algorithm>
 #include <cstdio>
+#include <thread>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -23,6 +24,19 @@
 #include "fsv_peaks.cuh"
 
 using namespace fsv;
+
+// FSV_TRACE=1: host-side phase times of every batch call on stderr
+#include <chrono>
+struct HostTrace {
+    bool on; std::chrono::steady_clock::time_point t;
+    HostTrace() : on(getenv("FSV_TRACE") != nullptr), t(std::chrono::steady_clock::now()) {}
+    void lap(const char* what) {
+        if (!on) return;
+        auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[fsv] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
 
 struct fsv_ctx {
     int device = 0;
@@ -47,7 +61,39 @@ struct fsv_ctx {
     int32_t* d_tables = nullptr; size_t tables_cap = 0;
     int32_t* d_free_stack = nullptr; size_t stack_cap = 0;
     int32_t* d_lazy = nullptr; size_t lazy_cap = 0;      // LazyState followed by the per-CTA slot index
+    // device blocks of destroyed batches, kept for the next one (cudaMalloc / cudaFree of GB-sized blocks
+    // cost tens of milliseconds per call and synchronise the device)
+    std::vector<std::pair<void*, size_t>> dcache;
 };
+
+static void* dev_alloc(fsv_ctx* c, size_t bytes, size_t* got)
+{
+    int best = -1;
+    for (size_t i = 0; i < c->dcache.size(); ++i) {
+        const size_t sz = c->dcache[i].second;
+        if (sz >= bytes && sz <= bytes + bytes / 2 + (1u << 20) && (best < 0 || sz < c->dcache[best].second)) best = (int)i;
+    }
+    if (best >= 0) {
+        void* p = c->dcache[best].first; *got = c->dcache[best].second;
+        c->dcache.erase(c->dcache.begin() + best);
+        return p;
+    }
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {      // make room: drop what is cached, retry once
+        cudaGetLastError();
+        for (auto& e : c->dcache) cudaFree(e.first);
+        c->dcache.clear();
+        if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    }
+    *got = bytes;
+    return p;
+}
+static void dev_release(fsv_ctx* c, void* p, size_t bytes)
+{
+    if (!p) return;
+    c->dcache.emplace_back(p, bytes);
+    while (c->dcache.size() > 24) { cudaFree(c->dcache.front().first); c->dcache.erase(c->dcache.begin()); }
+}
 
 // one fill-kernel launch: a slice of the work list, largest task first
 struct Launch { int kind /*0 general, 1 DPX*/, nw, with_tb, excl, begin, count, grid; int64_t table_off; };
@@ -88,6 +134,7 @@ struct fsv_batch {
     unsigned long long* d_cursor = nullptr;
     uint32_t* d_cigar = nullptr;
     long long* d_timeline = nullptr;
+    size_t sz_q = 0, sz_t = 0, sz_tasks = 0, sz_work = 0, sz_results = 0, sz_ctrl = 0, sz_cursor = 0, sz_cigar = 0, sz_timeline = 0;
     int state = 0;                    // 0 created, 1 run
 };
 
@@ -156,6 +203,7 @@ extern "C" void fsv_destroy(fsv_ctx* c)
     if (c->d_tables) cudaFree(c->d_tables);
     if (c->d_free_stack) cudaFree(c->d_free_stack);
     if (c->d_lazy) cudaFree(c->d_lazy);
+    for (auto& e : c->dcache) cudaFree(e.first);
     for (auto ks : c->kstream) if (ks) cudaStreamDestroy(ks);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -272,8 +320,12 @@ static int64_t pow2_at_least(int64_t x) { int64_t p = 1; while (p < x) p <<= 1; 
 
 static void free_batch_device(fsv_batch* b)
 {
-    cudaFree(b->d_q); cudaFree(b->d_t); cudaFree(b->d_tasks); cudaFree(b->d_work); cudaFree(b->d_results);
-    cudaFree(b->d_ctrl); cudaFree(b->d_cursor); cudaFree(b->d_cigar); cudaFree(b->d_timeline);
+    fsv_ctx* c = b->ctx;
+    dev_release(c, b->d_q, b->sz_q); dev_release(c, b->d_t, b->sz_t); dev_release(c, b->d_tasks, b->sz_tasks);
+    dev_release(c, b->d_work, b->sz_work); dev_release(c, b->d_results, b->sz_results); dev_release(c, b->d_ctrl, b->sz_ctrl);
+    dev_release(c, b->d_cursor, b->sz_cursor); dev_release(c, b->d_cigar, b->sz_cigar); dev_release(c, b->d_timeline, b->sz_timeline);
+    b->d_q = b->d_t = nullptr; b->d_tasks = nullptr; b->d_work = nullptr; b->d_results = nullptr; b->d_ctrl = nullptr;
+    b->d_cursor = nullptr; b->d_cigar = nullptr; b->d_timeline = nullptr;
 }
 
 extern "C" void fsv_batch_destroy(fsv_batch* b)
@@ -309,12 +361,35 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
     *out = nullptr;
     if (n > 0x7ffffff0u) return FSV_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
+    HostTrace tr;
     fsv_batch* b = new (std::nothrow) fsv_batch();
     if (!b) return FSV_ERR_NOMEM;
     b->ctx = c; b->n = n;
     bool all_reset; int reset_status;
     int rc = build_scoring(scoring, &b->sc, &b->dual, &reset_status, &all_reset);
     if (rc != FSV_OK) { delete b; return rc; }
+
+    // ---- which tasks hold a base outside A,C,G,T (the DPX kernel packs bases in 2 bits): the one pass
+    // over the caller's arenas, spread over host threads when they are large
+    std::vector<uint8_t> wild(n, 0);
+    if (!c->force_exact && n) {
+        auto scan = [&](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; ++i) {
+                const fsv_task& t = tasks[i];
+                if (t.qlen <= 0 || t.tlen <= 0 || t.q_off < 0 || t.t_off < 0 || (uint64_t)t.q_off + (uint64_t)t.qlen > qbytes ||
+                    (uint64_t)t.t_off + (uint64_t)t.tlen > tbytes) continue;
+                wild[i] = has_wildcard(qarena + t.q_off, (size_t)t.qlen) || has_wildcard(tarena + t.t_off, (size_t)t.tlen);
+            }
+        };
+        unsigned nthr = (qbytes + tbytes) > (8u << 20) ? std::min(16u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
+        if (nthr <= 1) scan(0, n);
+        else {
+            std::vector<std::thread> th;
+            for (unsigned k = 0; k < nthr; ++k) th.emplace_back(scan, n * k / nthr, n * (k + 1) / nthr);
+            for (auto& t : th) t.join();
+        }
+    }
+    tr.lap("create: wildcard scan");
 
     // ---- task table
     b->tasks.resize(n);
@@ -355,8 +430,7 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
         }
         if (!c->force_exact) {
             // the DPX kernel packs bases in 2 bits: a task with a wildcard base goes to the general kernel
-            const bool wild = has_wildcard(qarena + t.q_off, (size_t)t.qlen) || has_wildcard(tarena + t.t_off, (size_t)t.tlen);
-            if (dpx_supports(b->sc, d, wild)) {
+            if (dpx_supports(b->sc, d, wild[i] != 0)) {
                 b->is_dpx[i] = 1;
                 d.nw = dpx_class_of(dpx_warps_needed(d));
                 d.tb_mode = b->dual ? 4 : 2;
@@ -364,6 +438,7 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
         }
     }
     b->cigar_cap_words = cigar_words;
+    tr.lap("create: task table");
 
     // ---- traceback page pool: what the batch needs, capped by the budget
     {
@@ -434,6 +509,7 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
     for (int cls : {8, 6}) for (int with_tb = 1; with_tb >= 0; --with_tb) add_launch(1, cls, with_tb, 1);
     for (int cls : kClasses) for (int with_tb = 1; with_tb >= 0; --with_tb) add_launch(1, cls, with_tb, 0);
     add_launch(0, 0, 0, 0);
+    tr.lap("create: sort + work lists");
     b->ws_lanes = ws_need ? pow2_at_least(ws_need) : 0;
     if (b->launches.size() > 16) { delete b; return FSV_ERR_INVALID; }
 
@@ -448,15 +524,23 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
             return fail(e_ == cudaErrorMemoryAllocation ? FSV_ERR_NOMEM : FSV_ERR_CUDA);           \
         }                                                                                          \
     } while (0)
-    CKB(cudaMalloc(&b->d_q, qbytes + 64));
-    CKB(cudaMalloc(&b->d_t, tbytes + 64));
-    CKB(cudaMalloc(&b->d_tasks, (n + 1) * sizeof(DevTask)));
-    CKB(cudaMalloc(&b->d_work, (n + 1) * 4));
-    CKB(cudaMalloc(&b->d_results, (n + 1) * sizeof(fsv_result)));
-    CKB(cudaMalloc(&b->d_ctrl, 256));
-    CKB(cudaMalloc(&b->d_cursor, 64));
-    CKB(cudaMalloc(&b->d_cigar, (size_t)(b->cigar_cap_words + 4) * 4));
-    CKB(cudaMalloc(&b->d_timeline, (n + 1) * 16));
+#define DEV(ptr, szf, bytes)                                                                        \
+    do {                                                                                           \
+        void* p_ = dev_alloc(c, (bytes), &b->szf);                                                 \
+        if (!p_) { c->last_error = "device allocation of " + std::to_string((size_t)(bytes)) + " bytes failed"; return fail(FSV_ERR_NOMEM); } \
+        b->ptr = reinterpret_cast<decltype(b->ptr)>(p_);                                           \
+    } while (0)
+    DEV(d_q, sz_q, qbytes + 64);
+    DEV(d_t, sz_t, tbytes + 64);
+    DEV(d_tasks, sz_tasks, (n + 1) * sizeof(DevTask));
+    DEV(d_work, sz_work, (n + 1) * 4);
+    DEV(d_results, sz_results, (n + 1) * sizeof(fsv_result));
+    DEV(d_ctrl, sz_ctrl, 256);
+    DEV(d_cursor, sz_cursor, 64);
+    DEV(d_cigar, sz_cigar, (size_t)(b->cigar_cap_words + 4) * 4);
+    DEV(d_timeline, sz_timeline, (n + 1) * 16);
+#undef DEV
+    tr.lap("create: cudaMalloc");
     CKB(cudaMemsetAsync(b->d_timeline, 0, (n + 1) * 16, c->stream));
     if (qbytes) CKB(cudaMemcpyAsync(b->d_q, qarena, qbytes, cudaMemcpyHostToDevice, c->stream));
     if (tbytes) CKB(cudaMemcpyAsync(b->d_t, tarena, tbytes, cudaMemcpyHostToDevice, c->stream));
@@ -465,6 +549,7 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
         CKB(cudaMemcpyAsync(b->d_work, b->work.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
     }
     CKB(cudaStreamSynchronize(c->stream));
+    tr.lap("create: H2D");
 #undef CKB
     c->stats.h2d_bytes += (int64_t)(qbytes + tbytes + n * (sizeof(DevTask) + 4));
     *out = b;
@@ -485,6 +570,7 @@ extern "C" int fsv_batch_run(fsv_batch* b)
 {
     if (!b) return FSV_ERR_INVALID;
     fsv_ctx* c = b->ctx;
+    HostTrace tr;
     CK(c, cudaSetDevice(c->device));
     // ---- scratch: page pool, free stack, page tables, general-kernel windows
     int64_t tables = 0, ws_bytes = 0, n_slots = 0;
@@ -516,6 +602,7 @@ extern "C" int fsv_batch_run(fsv_batch* b)
         CK(c, cudaMemsetAsync(b->d_cursor, 0, 64, c->stream));
         CK(c, cudaStreamSynchronize(c->stream));      // `stack` and `ctrl` are stack/heap temporaries
     }
+    tr.lap("run: scratch + control block");
     RunCtx R{};
     R.qarena = b->d_q; R.tarena = b->d_t; R.tasks = b->d_tasks; R.results = b->d_results;
     R.pool.base = c->d_pool; R.pool.page_bytes = c->page_bytes; R.pool.n_pages = (int32_t)b->pool_pages;
@@ -565,6 +652,7 @@ extern "C" int fsv_batch_run(fsv_batch* b)
     }
     CK(c, cudaEventRecord(e1, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
+    tr.lap("run: kernels");
     float ms = 0;
     CK(c, cudaEventElapsedTime(&ms, e0, e1));
     for (auto e : done) cudaEventDestroy(e);
@@ -622,8 +710,11 @@ extern "C" int fsv_align_batch(fsv_ctx* c, const fsv_scoring* sc,
     int rc = fsv_batch_create(c, sc, qarena, qbytes, tarena, tbytes, tasks, n, &b);
     if (rc != FSV_OK) return rc;
     rc = fsv_batch_run(b);
+    HostTrace tr;
     if (rc == FSV_OK) rc = fsv_batch_fetch(b, out, cigar, cigar_cap, cigar_used);
+    tr.lap("fetch");
     fsv_batch_destroy(b);
+    tr.lap("destroy");
     return rc;
 }
 
