@@ -430,6 +430,7 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
         }
         if (!c->force_exact) {
             // the DPX kernel packs bases in 2 bits: a task with a wildcard base goes to the general kernel
+            d.wild = wild[i];
             if (dpx_supports(b->sc, d, wild[i] != 0)) {
                 b->is_dpx[i] = 1;
                 d.nw = dpx_class_of(dpx_warps_needed(d));

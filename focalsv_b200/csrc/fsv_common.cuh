@@ -30,6 +30,8 @@ struct DevTask {
     int32_t nw;             // DPX kernel: warps per task (0 = general kernel)
     int32_t tb_pages;       // traceback pages this task needs (0 = score only)
     int32_t rows_per_page;  // antidiagonals per page
+    int32_t wild;           // some base of the task is the wildcard (code > 3)
+    int32_t pad2_;
 };
 
 // where the CIGAR walk of a task starts (ksw2_extz2_sse.c:292-301)

@@ -102,7 +102,7 @@ template <bool DUAL>
 struct DpxConst {
     // tie-break codes in the low byte (higher wins): left alignment, ksw2_extz2_sse.c:177-181
     static constexpr uint32_t cS = DUAL ? 4 : 2, cE = DUAL ? 3 : 1, cF = DUAL ? 2 : 0, cE2 = 1, cF2 = 0;
-    uint32_t gU, gX, gY, gX2, gY2, sInit, sMch, sMis, kClamp, kQ, kQ2, kQE, kQE2, kBias;
+    uint32_t gU, gX, gY, gX2, gY2, sInit, sMch, sMis, sAmb, kClamp, kQ, kQ2, kQE, kQE2, kBias;
     int qe, qe2, bias, r0_bias;
     __device__ __forceinline__ explicit DpxConst(const DevScoring& sc)
     {
@@ -113,6 +113,7 @@ struct DpxConst {
         sInit = both((DUAL ? 0 : hi8(2 * qe)) | cS);                         // s[] starts at 0 (kcalloc)
         sMch = both((DUAL ? hi8(sc.sc_mch) : hi8(sc.sc_mch + 2 * qe)) | cS);
         sMis = both((DUAL ? hi8(sc.sc_mis) : hi8(sc.sc_mis + 2 * qe)) | cS);
+        sAmb = both((DUAL ? hi8(sc.sc_N) : hi8(sc.sc_N + 2 * qe)) | cS);      // either base is the wildcard m-1 (:68,130)
         kClamp = both(hi8(sc.max_sc_clamp));
         kQ = both(hi8(sc.q)); kQ2 = both(hi8(sc.q2)); kQE = both(hi8(qe)); kQE2 = both(hi8(qe2));
         bias = DUAL ? 0 : qe; r0_bias = DUAL ? qe : 2 * qe;
@@ -131,6 +132,15 @@ __device__ __forceinline__ void dpx_profile(uint32_t (&sv)[8], uint32_t tw, uint
         const uint32_t mm = prmt(sh, 0u, k < 4 ? 0xAA88u : 0xBB99u);   // 0xffff per mismatching half
         sv[k] = (mm & K.sMis) | (~mm & K.sMch);
     }
+}
+// the same for a task with wildcard bases: `amb` holds one bit per lane (target window in the high half,
+// query window in the low half); a lane where either base is the wildcard scores sc_N (:130-134)
+template <bool DUAL>
+__device__ __forceinline__ void dpx_profile_amb(uint32_t (&sv)[8], uint32_t amb, const DpxConst<DUAL>& K)
+{
+    const uint32_t bits = (amb | (amb >> 16)) & 0xffffu;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const uint32_t lm = prmt(bits << (7 - k), 0u, 0x9988u); sv[k] = (K.sAmb & lm) | (sv[k] & ~lm); }
 }
 
 // The recurrence on the 16 lanes of one vector (:26-47, :171-196), words 7..0 so that word k-1 is
@@ -198,7 +208,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
     constexpr int NT = NW * 32;
     using KC = DpxConst<DUAL>;
     // one shared block, addressed from a single base register:
-    //   edge slots [2 parities][NW] x 32 B : {x, v, x2, qw} of lane 15 of each warp's last vector, then its H
+    //   edge slots [2 parities][NW] x 32 B : {x, v, x2, qw} of lane 15 of each warp's last vector, then its H and wildcard bit
     //   per-warp max H, ring over 3 antidiagonals; tie key / H[en0] / H[st0] rings; stop flag; task index
     constexpr uint32_t OFF_EDGE = 0, OFF_MH = 2 * NW * 32, OFF_KEY = OFF_MH + 3 * NW * 4, OFF_HEN0 = OFF_KEY + 12,
                        OFF_HST0 = OFF_HEN0 + 12, OFF_STOP = OFF_HST0 + 12, OFF_TASK = OFF_STOP + 4, SH_BYTES = OFF_TASK + 4;
@@ -237,6 +247,8 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
         int32_t Hb = 0;
         int Vt = tid - NT;          // forces the (re)arm path on the first antidiagonal
         uint32_t tw = 0, qw = 0;
+        uint32_t amb = 0;           // wildcard bases of the two windows, one bit per lane: target << 16 | query (tasks with T.wild only)
+        const bool wild = T.wild != 0;
         uint32_t qpre = 0; int qpre_r = -1;     // query base the lowest vector of the band needs at antidiagonal qpre_r
         EzState ez; ez.reset();     // complete only in warp 0 (the bookkeeping warp)
         int64_t cells = 0;
@@ -261,6 +273,13 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
             uint32_t nbX = __shfl_up_sync(FULL, X[7], 1), nbV = __shfl_up_sync(FULL, V[7], 1);
             uint32_t nbX2 = DUAL ? __shfl_up_sync(FULL, X2[7], 1) : 0;
             uint32_t nbQ = __shfl_up_sync(FULL, qw, 1);
+            uint32_t nbA = 0;          // wildcard bit of the neighbour's lane 15 (query side)
+            if (wild) {
+                nbA = __shfl_up_sync(FULL, amb, 1);
+                if (NW == 1) { const uint32_t a2 = __shfl_sync(FULL, amb, 31); if (lane == 0) nbA = a2; }
+                else if (lane == 0 && r > 0) nbA = lds32(sb + OFF_EDGE + (uint32_t)(ppar * NW + (warp + NW - 1) % NW) * 32u + 20u);
+                nbA = (nbA >> 15) & 1u;
+            }
             if (NW == 1) {
                 uint32_t a = __shfl_sync(FULL, X[7], 31), b = __shfl_sync(FULL, V[7], 31);
                 uint32_t c2 = DUAL ? __shfl_sync(FULL, X2[7], 31) : 0, q2 = __shfl_sync(FULL, qw, 31);
@@ -355,6 +374,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                     const int base = Vt << 4;
                     qw = (qw << 2) | (nbQ >> 30);            // lane c now faces query[r - base - c]
                     dpx_profile<DUAL>(S, tw, qw, K);
+                    if (wild) { amb = (amb & 0xffff0000u) | (((amb << 1) | nbA) & 0xffffu); dpx_profile_amb<DUAL>(S, amb, K); }
                     const uint32_t XT0 = prmt(nbX, X[7], 0x5432u), VT0 = prmt(nbV, V[7], 0x5432u);
                     const uint32_t X2T0 = DUAL ? prmt(nbX2, X2[7], 0x5432u) : 0;
                     uint4 o;
@@ -389,7 +409,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
 #pragma unroll
                         for (int k = 0; k < 8; ++k) { U[k] = K.gU; V[k] = K.gU; X[k] = K.gX; Y[k] = K.gY; X2[k] = K.gX2; Y2[k] = K.gY2; S[k] = K.sInit; Hr[k] = 0; }
                         Hb = 0;
-                        tw = 0; qw = 0;
+                        tw = 0; qw = 0; amb = 0;
                         const int nb = Vt << 4;
                         for (int c = 0; c < 16; ++c) {
                             const int t = nb + c, j = r - t;
@@ -397,6 +417,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                             uint32_t qbse = (j >= 0 && j < qlen) ? query[j] : 0;
                             tw |= (tbse & 3u) << (2 * c);
                             qw |= (qbse & 3u) << (2 * c);
+                            amb |= ((tbse > 3u ? 0x10000u : 0u) | (qbse > 3u ? 1u : 0u)) << c;
                         }
                     }
                     // Everything below is straight-line code (selects and lane masks instead of branches), so
@@ -408,17 +429,19 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                     const bool lo_edge = Vt == st_, hi_edge = Vt == en_;
                     {   // lane c now faces query[r - base - c]; the lowest vector of the band reads its new base
                         // from memory, one antidiagonal ahead (qpre) so that the load is off the critical path
-                        if (lo_edge && !rearmed && qpre_r != r) { const int j = r - base; qpre = (j >= 0 && j < qlen) ? (uint32_t)(query[j] & 3u) : 0u; }
-                        const uint32_t q0 = lo_edge ? qpre : (nbQ >> 30);
+                        if (lo_edge && !rearmed && qpre_r != r) { const int j = r - base; const uint32_t c0 = (j >= 0 && j < qlen) ? (uint32_t)query[j] : 0u; qpre = (c0 & 3u) | (c0 > 3u ? 4u : 0u); }
+                        const uint32_t q0 = lo_edge ? (qpre & 3u) : (nbQ >> 30);
                         qw = rearmed ? qw : ((qw << 2) | q0);
+                        if (wild && !rearmed) amb = (amb & 0xffff0000u) | (((amb << 1) | (lo_edge ? (qpre >> 2) : nbA)) & 0xffffu);
                         int st0n, en0n;
                         band_limits(r + 1, qlen, tlen, w, st0n, en0n);
-                        if (Vt == (st0n >> 4)) { const int j = r + 1 - base; qpre = (j >= 0 && j < qlen) ? (uint32_t)(query[j] & 3u) : 0u; qpre_r = r + 1; }
+                        if (Vt == (st0n >> 4)) { const int j = r + 1 - base; const uint32_t c0 = (j >= 0 && j < qlen) ? (uint32_t)query[j] : 0u; qpre = (c0 & 3u) | (c0 > 3u ? 4u : 0u); qpre_r = r + 1; }
                     }
                     {   // profile stores (:126-140): whole 16-lane stores from st0, so the last one overhangs en0
                         const int store_end = st0 + ((en0 - st0) >> 4) * 16 + 15;
                         uint32_t sv[8];
                         dpx_profile<DUAL>(sv, tw, qw, K);
+                        if (wild) dpx_profile_amb<DUAL>(sv, amb, K);
                         const uint32_t bits = lane_bits(min(st0 - base, 16), store_end - base);      // 0 below st_ and above the overhang
 #pragma unroll
                         for (int k = 0; k < 8; ++k) { const uint32_t lm = word_mask(bits, k); S[k] = (sv[k] & lm) | (S[k] & ~lm); }
@@ -509,6 +532,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                     const uint32_t ea = sb + OFF_EDGE + (uint32_t)(par * NW + warp) * 32u;
                     sts128(ea, make_uint4(X[7], V[7], DUAL ? X2[7] : 0u, qw));
                     sts32(ea + 16u, (uint32_t)(Hb + sext16(Hr[7] >> 16)));
+                    if (wild) sts32(ea + 20u, amb);
                 }
                 const int32_t wmax = __reduce_max_sync(FULL, habs);
                 if (lane == 0) sts32(sb + OFF_MH + 4u * (uint32_t)(s3 * NW + warp), (uint32_t)wmax);
@@ -556,7 +580,8 @@ inline int dpx_class_of(int warps)
 // `has_wild` = some base of the task is not A/C/G/T (code > 3)
 inline bool dpx_supports(const DevScoring& sc, const DevTask& t, bool has_wild)
 {
-    if (t.kind != 1 || has_wild) return false;
+    (void)has_wild;            // wildcard bases: one extra bit per lane in the kernel (T.wild)
+    if (t.kind != 1) return false;
     if (t.flag & (FSV_EZ_GENERIC_SC | FSV_EZ_RIGHT | FSV_EZ_APPROX_MAX | FSV_EZ_APPROX_DROP)) return false;
     if (sc.m != 5) return false;
     return dpx_class_of(dpx_warps_needed(t)) != 0;

@@ -246,9 +246,37 @@ def test_small_pages_and_tight_pool(oracle):
         al.close()
 
 
+@pytest.mark.parametrize("preset,w", [("asm5", 3001), ("hifiasm", 500), ("map-ont", 40)])
+def test_wildcard_bases_on_the_dpx_kernel(oracle, aligner, preset, w):
+    """N bases (code 4, scored sc_N, ksw2_extz2_sse.c:68,130-134) in the query, the target or both: isolated,
+    in runs that cross 16-lane vectors and warps, and at the ends; the tasks stay on the DPX kernel."""
+    rng = np.random.default_rng(77 + w)
+    pairs = []
+    for i, L in enumerate([700, 1500, 2600, 4100, 5200, 6400]):
+        ref = synth.random_seq(rng, L)
+        q = synth.mutate(rng, ref, 0.01, 0.004, 0.004).copy()
+        ref = ref.copy()
+        if i % 3 != 1:
+            q[rng.integers(0, len(q), len(q) // 30)] = 4
+            k = int(rng.integers(0, len(q) - 200)); q[k:k + int(rng.integers(1, 150))] = 4
+        if i % 3 != 0:
+            ref[rng.integers(0, len(ref), len(ref) // 40)] = 4
+            k = int(rng.integers(0, len(ref) - 700)); ref[k:k + int(rng.integers(1, 600))] = 4
+        if i == 4:
+            q[:3] = 4; q[-2:] = 4; ref[0] = 4; ref[-1] = 4
+        pairs.append((q, ref))
+    flags = np.array([0, _abi.EZ_EXTZ_ONLY, 0, _abi.EZ_SCORE_ONLY, _abi.EZ_REV_CIGAR, 0], dtype=np.int32)
+    from focalsv_b200.presets import PRESETS
+    g = synth._pack("wild." + preset, preset, pairs, w, PRESETS[preset].zdrop, flags=flags)
+    before = aligner.stats()["exact_path_tasks"]
+    bad, ores, gres = compare_group(oracle, aligner, g)
+    assert not bad, bad
+    assert aligner.stats()["exact_path_tasks"] == before
+
+
 def test_mixed_kernel_variants_share_the_pool(oracle, aligner):
     """One batch whose tasks land on several kernel variants at once (1/2/4-warp DPX classes, score-only and
-    CIGAR, and wildcard tasks on the general kernel), all running concurrently on one page pool."""
+    CIGAR, wildcard tasks, and right-aligned tasks on the general kernel), all running concurrently on one page pool."""
     rng = np.random.default_rng(321)
     pairs, flags = [], []
     for i in range(48):
@@ -256,7 +284,7 @@ def test_mixed_kernel_variants_share_the_pool(oracle, aligner):
         ref = synth.random_seq(rng, L)
         q = synth.mutate(rng, ref, 0.01, 0.004, 0.004)
         if i % 7 == 0:
-            q = q.copy(); q[:: 50] = 4          # wildcard bases -> general kernel
+            q = q.copy(); q[:: 50] = 4          # wildcard bases
         pairs.append((q, ref)); flags.append([0, _abi.EZ_SCORE_ONLY, _abi.EZ_EXTZ_ONLY, _abi.EZ_RIGHT][i % 4])
     g = synth._pack("mixed", "map-ont", pairs, -1, 400, flags=np.array(flags, dtype=np.int32))
     tasks = g.tasks.copy()
