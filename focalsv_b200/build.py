@@ -1,19 +1,24 @@
 """Build libfocalsv_cuda.so in-tree for sm_100a (nvcc cross-compiles without a GPU).
 
 The shared object lands next to this file (focalsv_b200/libfocalsv_cuda.so): it is
-git-ignored but travels to the GPU box with the gpurun snapshot.
+git-ignored but travels to the GPU box with the gpurun snapshot.  The DPX fill kernel is
+compiled as six translation units (dual x traceback mode), in parallel, then linked with the
+C ABI (fsv_capi.cu).
 """
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libfocalsv_cuda.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC,-O3,-Wall", "-shared", "--use_fast_math", "-Xptxas", "-v",
-         "-I", os.path.join(HERE, "..", "include")]
+CFLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+          "-Xcompiler", "-fPIC,-O3,-Wall", "--use_fast_math", "-Xptxas", "-v",
+          "-I", os.path.join(HERE, "..", "include")]
+VARIANTS = [(d, t) for d in (0, 1) for t in (0, 1, 2)]
 
 
 def sources():
@@ -24,36 +29,54 @@ def stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = sources() + [os.path.join(HERE, "..", "include", "focalsv_cuda.h")]
+    deps = sources() + [os.path.join(HERE, "..", "include", "focalsv_cuda.h"), os.path.abspath(__file__)]
     return any(os.path.getmtime(s) > t for s in deps)
+
+
+def _units(defs):
+    units = [("capi", os.path.join(CSRC, "fsv_capi.cu"), [])]
+    for d, t in VARIANTS:
+        units.append(("dpx_%d%d" % (d, t), os.path.join(CSRC, "fsv_dpx_variant.cu"),
+                      ["-DFSV_VARIANT_DUAL=%d" % d, "-DFSV_VARIANT_TBM=%d" % t]))
+    return [(n, s, f + list(defs)) for n, s, f in units]
+
+
+def _compile(objdir, name, src, flags):
+    obj = os.path.join(objdir, name + ".o")
+    r = subprocess.run([NVCC] + CFLAGS + flags + ["-c", "-o", obj, src], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    return name, obj, r.returncode, r.stdout
+
+
+def _build(out, defs, objdir, log):
+    os.makedirs(objdir, exist_ok=True)
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
+        res = list(ex.map(lambda u: _compile(objdir, *u), _units(defs)))
+    text = "".join("==== %s\n%s" % (n, o) for n, _, _, o in res)
+    if log:
+        with open(log, "w") as fh:
+            fh.write(text)
+    if any(rc for _, _, rc, _ in res):
+        sys.stderr.write(text)
+        raise RuntimeError("nvcc failed" + (" (see %s)" % log if log else ""))
+    r = subprocess.run([NVCC, "-shared", "-o", out] + [o for _, o, _, _ in res], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("link failed")
+    return out
 
 
 def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
-    cmd = [NVCC] + FLAGS + ["-o", LIB, os.path.join(CSRC, "fsv_capi.cu")]
+    _build(LIB, [], OBJ, os.path.join(HERE, "build.log"))
     if verbose:
-        print(" ".join(cmd))
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    log = os.path.join(HERE, "build.log")
-    with open(log, "w") as fh:
-        fh.write(r.stdout)
-    if r.returncode != 0:
-        sys.stderr.write(r.stdout)
-        raise RuntimeError("nvcc failed (see %s)" % log)
-    if verbose:
-        print(r.stdout)
+        print(open(os.path.join(HERE, "build.log")).read())
     return LIB
 
 
 def build_variant(out, defs):
     """Experiment builds: same sources with extra -D flags into another file (scripts/ only)."""
-    cmd = [NVCC] + FLAGS + list(defs) + ["-o", out, os.path.join(CSRC, "fsv_capi.cu")]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if r.returncode != 0:
-        sys.stderr.write(r.stdout)
-        raise RuntimeError("nvcc failed")
-    return out
+    return _build(out, defs, OBJ + "_" + os.path.basename(out), None)
 
 
 if __name__ == "__main__":
@@ -61,4 +84,4 @@ if __name__ == "__main__":
         i = sys.argv.index("--variant")
         print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
     else:
-        print(build(force="--force" in sys.argv, verbose=True))
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

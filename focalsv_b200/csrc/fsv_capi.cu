@@ -43,7 +43,7 @@ struct fsv_ctx {
     int sm_count = 0;
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;            // copies, timing events
-    cudaStream_t kstream[16] = {};            // one per concurrently running fill-kernel variant
+    cudaStream_t kstream[32] = {};            // one per concurrently running fill-kernel variant
     std::string last_error;
     fsv_stats stats{};
     // options
@@ -434,7 +434,7 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
             if (dpx_supports(b->sc, d, wild[i] != 0)) {
                 b->is_dpx[i] = 1;
                 d.nw = dpx_class_of(dpx_warps_needed(d));
-                d.tb_mode = b->dual ? 4 : 2;
+                d.tb_mode = (t.flag & FSV_EZ_RIGHT) ? 0 : b->dual ? 4 : 2;      // right alignment stores ksw2's d itself
             }
         }
     }
@@ -495,24 +495,24 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
             const int ti = ord[k];
             const DevTask& d = b->tasks[ti];
             if (kind == 0) { if (b->is_dpx[ti]) continue; }
-            else if (!b->is_dpx[ti] || d.nw != nw || (int)!(d.flag & FSV_EZ_SCORE_ONLY) != with_tb || (int)is_excl[ti] != excl) continue;
+            else if (!b->is_dpx[ti] || d.nw != nw || ((d.flag & FSV_EZ_SCORE_ONLY) ? 0 : (d.flag & FSV_EZ_RIGHT) ? 2 : 1) != with_tb || (int)is_excl[ti] != excl) continue;
             b->work.push_back(ti);
             if (kind == 0 && d.kind == 1 && d.pitch + 96 > c->exact_smem_lanes) ws_need = std::max<int64_t>(ws_need, d.pitch + 96);
         }
         L.count = (int)b->work.size() - L.begin;
         if (!L.count) return;
-        L.grid = kind == 0 ? exact_grid(c, b->dual, L.count) : excl ? std::min(L.count, c->sm_count) : dpx_grid(c->sm_count, b->dual, with_tb != 0, nw, L.count);
+        L.grid = kind == 0 ? exact_grid(c, b->dual, L.count) : excl ? std::min(L.count, c->sm_count) : dpx_grid(c->sm_count, b->dual, with_tb, nw, L.count);
         L.table_off = table_off;
         table_off += (int64_t)L.grid * b->max_pages_per_task;
         b->launches.push_back(L);
     };
     static const int kClasses[5] = {8, 6, 4, 2, 1};
-    for (int cls : {8, 6}) for (int with_tb = 1; with_tb >= 0; --with_tb) add_launch(1, cls, with_tb, 1);
-    for (int cls : kClasses) for (int with_tb = 1; with_tb >= 0; --with_tb) add_launch(1, cls, with_tb, 0);
+    for (int cls : {8, 6}) for (int with_tb = 2; with_tb >= 0; --with_tb) add_launch(1, cls, with_tb, 1);
+    for (int cls : kClasses) for (int with_tb = 2; with_tb >= 0; --with_tb) add_launch(1, cls, with_tb, 0);
     add_launch(0, 0, 0, 0);
     tr.lap("create: sort + work lists");
     b->ws_lanes = ws_need ? pow2_at_least(ws_need) : 0;
-    if (b->launches.size() > 16) { delete b; return FSV_ERR_INVALID; }
+    if (b->launches.size() > 32) { delete b; return FSV_ERR_INVALID; }
 
     // ---- device buffers + H2D
     auto fail = [&](int code) { free_batch_device(b); delete b; return code; };
@@ -536,7 +536,7 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
     DEV(d_tasks, sz_tasks, (n + 1) * sizeof(DevTask));
     DEV(d_work, sz_work, (n + 1) * 4);
     DEV(d_results, sz_results, (n + 1) * sizeof(fsv_result));
-    DEV(d_ctrl, sz_ctrl, 256);
+    DEV(d_ctrl, sz_ctrl, 512);
     DEV(d_cursor, sz_cursor, 64);
     DEV(d_cigar, sz_cigar, (size_t)(b->cigar_cap_words + 4) * 4);
     DEV(d_timeline, sz_timeline, (n + 1) * 16);
@@ -593,7 +593,7 @@ extern "C" int fsv_batch_run(fsv_batch* b)
         std::vector<int32_t> stack((size_t)b->pool_pages + 1);
         for (int64_t i = 0; i < b->pool_pages; ++i) stack[(size_t)i] = (int32_t)i;
         CK(c, cudaMemcpyAsync(c->d_free_stack, stack.data(), (size_t)(b->pool_pages + 1) * 4, cudaMemcpyHostToDevice, c->stream));
-        int32_t ctrl[64] = {0};
+        int32_t ctrl[128] = {0};
         ctrl[2] = (int32_t)b->pool_pages;
         for (size_t i = 0; i < b->launches.size(); ++i) {
             unsigned long long st = (unsigned long long)(unsigned)b->launches[i].count;    // head 0, tail count
@@ -636,8 +636,8 @@ extern "C" int fsv_batch_run(fsv_batch* b)
         R.page_tables = c->d_tables + L.table_off;
         R.slot_base = slot_base; slot_base += L.grid;
         if (L.kind == 1) {
-            DpxParams D{R, Q};
-            rc = dpx_launch(ks, b->dual, L.with_tb != 0, L.nw, L.grid, L.excl != 0, D, &c->last_error);
+            DpxParams D{R, Q, DpxK{}};
+            rc = dpx_launch(ks, b->dual, L.with_tb, L.nw, L.grid, L.excl != 0, D, &c->last_error);
             if (rc != FSV_OK) return rc;
         } else {
             FillParams P{R, Q, c->d_ws, b->ws_lanes, c->exact_smem_lanes};

@@ -227,7 +227,7 @@ __device__ inline bool pool_lazy_admit(const TbPool& P, int slot, int total, int
     return ok;
 }
 // One more page for the lazy task of CTA slot `slot` (table[held] receives it).
-__device__ inline bool pool_lazy_grab(const TbPool& P, int slot, int32_t* table, int& held)
+static __device__ __noinline__ bool pool_lazy_grab(const TbPool& P, int slot, int32_t* table, int& held)
 {
     bool ok = false;
     pool_lock(P.lock);
@@ -382,6 +382,16 @@ __device__ inline int next_task(const RunCtx& C, const TaskQueue& Q, int32_t* ta
         if (task_pages(C, t, table, lazy_ok, held)) return t;
         pending = t;
     }
+}
+
+// A lazily growing task keeps one page ahead of the antidiagonal it is writing (thread 0 only; spins while the
+// grant would not be safe).  Out of line: this is rare code that must not cost the fill loop registers.
+static __device__ __noinline__ int pool_lazy_grow(const TbPool& P, int slot, int32_t* table, int held, int want)
+{
+    StallWatch watch;
+    while (held < want)
+        if (!pool_lazy_grab(P, slot, table, held)) { __nanosleep(4000); watch.poll(P); }
+    return held;
 }
 
 // byte address of traceback row r of a task (rows_per_page = page_bytes / pitch)

@@ -30,9 +30,18 @@ namespace fsv {
 
 constexpr int DPX_MAX_WARPS = 8;
 
+// scoring constants in the "int8 in the high byte of a 16-bit half" format.  Built on the HOST per launch and
+// passed in the kernel parameters, so that the fill loop reads them as constant-bank operands instead of
+// holding (or rebuilding) fifteen registers.
+struct DpxK {
+    uint32_t gU, gX, gY, gX2, gY2, sInit, sMch, sMis, sAmb, kClamp, kQ, kQ2, kQE, kQE2, kBias;
+    int qe, qe2, bias, r0_bias;
+};
+
 struct DpxParams {
     RunCtx C;
     TaskQueue Q;
+    DpxK K;
 };
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
@@ -41,8 +50,8 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(s));
     return d;
 }
-__device__ __forceinline__ uint32_t hi8(int v) { return ((uint32_t)v & 0xffu) << 8; }       // int8 -> high byte of a half
-__device__ __forceinline__ uint32_t both(uint32_t h) { return (h & 0xffffu) * 0x00010001u; } // same half twice
+__host__ __device__ __forceinline__ uint32_t hi8(int v) { return ((uint32_t)v & 0xffu) << 8; }       // int8 -> high byte of a half
+__host__ __device__ __forceinline__ uint32_t both(uint32_t h) { return (h & 0xffffu) * 0x00010001u; } // same half twice
 __device__ __forceinline__ int sext16(uint32_t h) { return (int)(int16_t)(uint16_t)h; }
 
 // Lane c of a vector lives in half (c >> 3) of word (c & 7).  Both accessors use static register
@@ -97,14 +106,14 @@ __device__ __forceinline__ void atom_min_shared(uint32_t a, uint32_t v) { asm vo
 // resident CTAs per SM the register budget is tuned for
 template <int NW> struct DpxOcc { static constexpr int value = NW == 1 ? 12 : NW == 2 ? 6 : NW == 4 ? 3 : 2; };
 
-// scoring constants in the "int8 in the high byte of a 16-bit half" format
-template <bool DUAL>
-struct DpxConst {
-    // tie-break codes in the low byte (higher wins): left alignment, ksw2_extz2_sse.c:177-181
-    static constexpr uint32_t cS = DUAL ? 4 : 2, cE = DUAL ? 3 : 1, cF = DUAL ? 2 : 0, cE2 = 1, cF2 = 0;
-    uint32_t gU, gX, gY, gX2, gY2, sInit, sMch, sMis, sAmb, kClamp, kQ, kQ2, kQE, kQE2, kBias;
-    int qe, qe2, bias, r0_bias;
-    __device__ __forceinline__ explicit DpxConst(const DevScoring& sc)
+template <bool DUAL, bool RIGHT = false>
+struct DpxConst : DpxK {
+    // tie-break codes in the low byte (higher wins).  Left alignment (ksw2_extz2_sse.c:177-181): M > E > F > E~ > F~,
+    // the traceback stores the code and the CIGAR walk turns it back into ksw2's d (tb_mode).  Right alignment
+    // (KSW_EZ_RIGHT, :203-207): the later state wins a tie, so the code IS ksw2's d.
+    static constexpr uint32_t cS = RIGHT ? 0 : DUAL ? 4 : 2, cE = RIGHT ? 1 : DUAL ? 3 : 1, cF = RIGHT ? 2 : DUAL ? 2 : 0,
+                              cE2 = RIGHT ? 3 : 1, cF2 = RIGHT ? 4 : 0;
+    __host__ __device__ explicit DpxConst(const DevScoring& sc)
     {
         qe = sc.q + sc.e; qe2 = sc.q2 + sc.e2;
         gU = both(DUAL ? hi8(-qe) : 0);                                      // initial u, v (:84 / dual memset)
@@ -122,8 +131,8 @@ struct DpxConst {
 };
 
 // score profile of the 16 lanes of a vector from the 2-bit packed target / query windows (:125-140)
-template <bool DUAL>
-__device__ __forceinline__ void dpx_profile(uint32_t (&sv)[8], uint32_t tw, uint32_t qw, const DpxConst<DUAL>& K)
+template <bool DUAL, bool RIGHT>
+__device__ __forceinline__ void dpx_profile(uint32_t (&sv)[8], uint32_t tw, uint32_t qw, const DpxK& K)
 {
     const uint32_t xr = tw ^ qw, ne = xr | (xr >> 1);             // bit 2c set <=> lane c mismatches
 #pragma unroll
@@ -135,8 +144,8 @@ __device__ __forceinline__ void dpx_profile(uint32_t (&sv)[8], uint32_t tw, uint
 }
 // the same for a task with wildcard bases: `amb` holds one bit per lane (target window in the high half,
 // query window in the low half); a lane where either base is the wildcard scores sc_N (:130-134)
-template <bool DUAL>
-__device__ __forceinline__ void dpx_profile_amb(uint32_t (&sv)[8], uint32_t amb, const DpxConst<DUAL>& K)
+template <bool DUAL, bool RIGHT>
+__device__ __forceinline__ void dpx_profile_amb(uint32_t (&sv)[8], uint32_t amb, const DpxK& K)
 {
     const uint32_t bits = (amb | (amb >> 16)) & 0xffffu;
 #pragma unroll
@@ -145,12 +154,12 @@ __device__ __forceinline__ void dpx_profile_amb(uint32_t (&sv)[8], uint32_t amb,
 
 // The recurrence on the 16 lanes of one vector (:26-47, :171-196), words 7..0 so that word k-1 is
 // still "old" when word k reads it.  XT0/VT0/X2T0 are the t-1 operands of word 0.
-template <bool DUAL, bool TB>
+template <bool DUAL, bool TB, bool RIGHT>
 __device__ __forceinline__ void dpx_cells(uint32_t (&U)[8], uint32_t (&V)[8], uint32_t (&X)[8], uint32_t (&Y)[8],
                                           uint32_t (&X2)[8], uint32_t (&Y2)[8], const uint32_t (&S)[8],
-                                          uint32_t XT0, uint32_t VT0, uint32_t X2T0, const DpxConst<DUAL>& K, uint4& tbo)
+                                          uint32_t XT0, uint32_t VT0, uint32_t X2T0, const DpxK& K, uint4& tbo)
 {
-    using C = DpxConst<DUAL>;
+    using C = DpxConst<DUAL, RIGHT>;
     const uint32_t fE = both(C::cE), fF = both(C::cF), fE2 = both(C::cE2), fF2 = both(C::cF2);      // max(.,0) floors
     // min(x, code | bit) is `code` when x's value byte is 0 and `code | bit` otherwise: the continuation bit of
     // ksw2.h:116-118 lands at its final position (0x08 E, 0x10 F, 0x20 E~, 0x40 F~) with one VIMNMX each
@@ -178,19 +187,35 @@ __device__ __forceinline__ void dpx_cells(uint32_t (&U)[8], uint32_t (&V)[8], ui
         U[k] = __vsub2(zc, vt1);
         V[k] = __vsub2(zc, ut);
         const uint32_t n1 = __vsub2(K.kQ, zc);
-        const uint32_t xa = __viaddmax_s16x2(a, n1, fE), ya = __viaddmax_s16x2(b, n1, fF);
         uint32_t fl = 0;
-        if (DUAL) {
-            const uint32_t n2 = __vsub2(K.kQ2, zc);
-            const uint32_t xa2 = __viaddmax_s16x2(a2, n2, fE2), ya2 = __viaddmax_s16x2(b2, n2, fF2);
-            X[k] = __vsub2(xa, K.kQE); Y[k] = __vsub2(ya, K.kQE);
-            X2[k] = __vsub2(xa2, K.kQE2); Y2[k] = __vsub2(ya2, K.kQE2);
-            if (TB) fl = __vmins2(xa, oE) + __vmins2(ya, oF) + __vmins2(xa2, oE2) + __vmins2(ya2, oF2);
+        if (RIGHT) {
+            // right alignment sets a continuation bit when the gap value is >= 0 BEFORE the max with 0 (:212-218),
+            // so the sum is kept and its sign bits are moved to 0x08 / 0x10 / 0x20 / 0x40
+            const uint32_t pe = __vadd2(a, n1), pf = __vadd2(b, n1);
+            const uint32_t xa = __vmaxs2(pe, fE), ya = __vmaxs2(pf, fF);
+            fl = ((~pe >> 12) & 0x00080008u) | ((~pf >> 11) & 0x00100010u);
+            if (DUAL) {
+                const uint32_t n2 = __vsub2(K.kQ2, zc);
+                const uint32_t pe2 = __vadd2(a2, n2), pf2 = __vadd2(b2, n2);
+                const uint32_t xa2 = __vmaxs2(pe2, fE2), ya2 = __vmaxs2(pf2, fF2);
+                X[k] = __vsub2(xa, K.kQE); Y[k] = __vsub2(ya, K.kQE);
+                X2[k] = __vsub2(xa2, K.kQE2); Y2[k] = __vsub2(ya2, K.kQE2);
+                fl |= ((~pe2 >> 10) & 0x00200020u) | ((~pf2 >> 9) & 0x00400040u);
+            } else { X[k] = xa; Y[k] = ya; }
         } else {
-            X[k] = xa; Y[k] = ya;
-            if (TB) fl = __vmins2(xa, oE) + __vmins2(ya, oF);
+            const uint32_t xa = __viaddmax_s16x2(a, n1, fE), ya = __viaddmax_s16x2(b, n1, fF);
+            if (DUAL) {
+                const uint32_t n2 = __vsub2(K.kQ2, zc);
+                const uint32_t xa2 = __viaddmax_s16x2(a2, n2, fE2), ya2 = __viaddmax_s16x2(b2, n2, fF2);
+                X[k] = __vsub2(xa, K.kQE); Y[k] = __vsub2(ya, K.kQE);
+                X2[k] = __vsub2(xa2, K.kQE2); Y2[k] = __vsub2(ya2, K.kQE2);
+                if (TB) fl = __vmins2(xa, oE) + __vmins2(ya, oF) + __vmins2(xa2, oE2) + __vmins2(ya2, oF2);
+            } else {
+                X[k] = xa; Y[k] = ya;
+                if (TB) fl = __vmins2(xa, oE) + __vmins2(ya, oF);
+            }
         }
-        if (TB) tbw[k] = (fl & 0x00780078u) | code;      // the low 3 bits of fl hold the sum of the codes (< 8)
+        if (TB) tbw[k] = (fl & 0x00780078u) | code;      // (left) the low 3 bits of fl hold the sum of the codes (< 8)
     }
     if (TB) {   // 16 traceback bytes in lane order (:195)
         const uint32_t a01 = prmt(tbw[0], tbw[1], 0x6240u), a23 = prmt(tbw[2], tbw[3], 0x6240u);
@@ -202,36 +227,41 @@ __device__ __forceinline__ void dpx_cells(uint32_t (&U)[8], uint32_t (&V)[8], ui
 
 // EXCL only tags a second copy of the 6- and 8-warp kernels: it is launched with (almost) all of an SM's
 // shared memory reserved, so that a CTA working on one of the few very long tasks has its SM to itself.
-template <bool DUAL, bool TB, int NW, bool EXCL = false>
-__global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kernel(const DpxParams P)
+// TBM: 0 = score only, 1 = traceback, ties to the left (default), 2 = traceback, ties to the right (KSW_EZ_RIGHT).
+template <bool DUAL, int TBM, int NW, bool EXCL = false>
+__global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kernel(const __grid_constant__ DpxParams P)
 {
     constexpr int NT = NW * 32;
-    using KC = DpxConst<DUAL>;
+    constexpr bool TB = TBM != 0, RIGHT = TBM == 2;
+    using KC = DpxConst<DUAL, RIGHT>;
     // one shared block, addressed from a single base register:
     //   edge slots [2 parities][NW] x 32 B : {x, v, x2, qw} of lane 15 of each warp's last vector, then its H and wildcard bit
-    //   per-warp max H, ring over 3 antidiagonals; tie key / H[en0] / H[st0] rings; stop flag; task index
+    //   per-warp max H, ring over 3 antidiagonals; tie key / H[en0] / H[st0] rings; stop flag; task index;
+    //   traceback pages the task holds (thread 0's; fewer than tb_pages = a lazily growing task)
     constexpr uint32_t OFF_EDGE = 0, OFF_MH = 2 * NW * 32, OFF_KEY = OFF_MH + 3 * NW * 4, OFF_HEN0 = OFF_KEY + 12,
-                       OFF_HST0 = OFF_HEN0 + 12, OFF_STOP = OFF_HST0 + 12, OFF_TASK = OFF_STOP + 4, SH_BYTES = OFF_TASK + 4;
+                       OFF_HST0 = OFF_HEN0 + 12, OFF_STOP = OFF_HST0 + 12, OFF_TASK = OFF_STOP + 4, OFF_HELD = OFF_TASK + 4, SH_BYTES = OFF_HELD + 4;
     __shared__ __align__(16) uint32_t sh_raw[(SH_BYTES + 15) / 16 * 4];
     const uint32_t sb = (uint32_t)__cvta_generic_to_shared(sh_raw);
     const RunCtx& C = P.C;
     const DevScoring& sc = C.sc;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
-    const DpxConst<DUAL> K(sc);
+    const DpxK& K = P.K;
     const uint32_t extSel = DUAL ? 0xB391u : 0x4341u;                  // int8 (signed / unsigned) -> int16
     int32_t* table = C.page_tables + (int64_t)blockIdx.x * C.max_pages_per_task;
     int pending = -1;
-    int tb_held = 0;            // thread 0: traceback pages this task holds (fewer than tb_pages: a lazily growing task)
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) { sts32(sb + OFF_TASK, (uint32_t)next_task(C, P.Q, table, pending, true, tb_held)); sts32(sb + OFF_STOP, (uint32_t)INT32_MAX); }
+        if (tid == 0) {
+            int held = 0;
+            sts32(sb + OFF_TASK, (uint32_t)next_task(C, P.Q, table, pending, true, held));
+            sts32(sb + OFF_STOP, (uint32_t)INT32_MAX); sts32(sb + OFF_HELD, (uint32_t)held);
+        }
         __syncthreads();
         const int ti = (int)lds32(sb + OFF_TASK);
         if (ti < 0) return;
         const DevTask T = C.tasks[ti];
-        const bool tb_lazy = tid == 0 && tb_held < T.tb_pages;      // (thread 0) pages are taken as the antidiagonals advance
         if (tid == 0 && C.timeline) C.timeline[2 * T.orig] = global_ns();
         const int qlen = T.qlen, tlen = T.tlen, w = T.w;
         const uint8_t* query = C.qarena + T.q_off;
@@ -252,7 +282,6 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
         uint32_t qpre = 0; int qpre_r = -1;     // query base the lowest vector of the band needs at antidiagonal qpre_r
         EzState ez; ez.reset();     // complete only in warp 0 (the bookkeeping warp)
         int64_t cells = 0;
-        int last_st = -1, last_en = -1;
         int32_t hprev_keep = 0;     // H[en0-1] as last seen while that lane was inside the band
         // The ksw_extz_t bookkeeping of antidiagonal d is finished two iterations later (d+2), by warp 0
         // only: the maximum of d crosses the CTA through shared memory behind the ONE barrier of
@@ -373,12 +402,12 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                 if (__all_sync(FULL, inner)) {
                     const int base = Vt << 4;
                     qw = (qw << 2) | (nbQ >> 30);            // lane c now faces query[r - base - c]
-                    dpx_profile<DUAL>(S, tw, qw, K);
-                    if (wild) { amb = (amb & 0xffff0000u) | (((amb << 1) | nbA) & 0xffffu); dpx_profile_amb<DUAL>(S, amb, K); }
+                    dpx_profile<DUAL, RIGHT>(S, tw, qw, K);
+                    if (wild) { amb = (amb & 0xffff0000u) | (((amb << 1) | nbA) & 0xffffu); dpx_profile_amb<DUAL, RIGHT>(S, amb, K); }
                     const uint32_t XT0 = prmt(nbX, X[7], 0x5432u), VT0 = prmt(nbV, V[7], 0x5432u);
                     const uint32_t X2T0 = DUAL ? prmt(nbX2, X2[7], 0x5432u) : 0;
                     uint4 o;
-                    dpx_cells<DUAL, TB>(U, V, X, Y, X2, Y2, S, XT0, VT0, X2T0, K, o);
+                    dpx_cells<DUAL, TB, RIGHT>(U, V, X, Y, X2, Y2, S, XT0, VT0, X2T0, K, o);
                     if (TB) *reinterpret_cast<uint4*>(tb_page + (int64_t)tb_rip * T.pitch + (base - st)) = o;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {            // H[t] += v[t] - qe (:239-241)
@@ -440,8 +469,8 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                     {   // profile stores (:126-140): whole 16-lane stores from st0, so the last one overhangs en0
                         const int store_end = st0 + ((en0 - st0) >> 4) * 16 + 15;
                         uint32_t sv[8];
-                        dpx_profile<DUAL>(sv, tw, qw, K);
-                        if (wild) dpx_profile_amb<DUAL>(sv, amb, K);
+                        dpx_profile<DUAL, RIGHT>(sv, tw, qw, K);
+                        if (wild) dpx_profile_amb<DUAL, RIGHT>(sv, amb, K);
                         const uint32_t bits = lane_bits(min(st0 - base, 16), store_end - base);      // 0 below st_ and above the overhang
 #pragma unroll
                         for (int k = 0; k < 8; ++k) { const uint32_t lm = word_mask(bits, k); S[k] = (sv[k] & lm) | (S[k] & ~lm); }
@@ -452,7 +481,8 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                         uint32_t X2T0 = DUAL ? prmt(nbX2, X2[7], 0x5432u) : 0;
                         const int ce = en0 - base; // lane of en0 inside this vector (meaningful when hi_edge)
                         {   // carries of the lowest vector (:118-122)
-                            const bool inl = st > 0 && st - 1 >= last_st && st - 1 <= last_en;
+                            // [last_st, last_en] = rounded range of the previous antidiagonal (:287), rebuilt from its exact limits
+                            const bool inl = st > 0 && st - 1 >= round_st(st0p) && st - 1 <= round_en(en0p);
                             uint32_t vfirst;       // first column: v1 of an antidiagonal that starts at t = 0
                             if (DUAL) vfirst = hi8(r == 0 ? -K.qe : r < sc.long_thres ? -sc.e : r == sc.long_thres ? sc.long_diff : -sc.e2);
                             else vfirst = hi8(r ? sc.q : 0);
@@ -484,7 +514,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                         }
 
                         uint4 o;
-                        dpx_cells<DUAL, TB>(U, V, X, Y, X2, Y2, S, XT0, VT0, X2T0, K, o);
+                        dpx_cells<DUAL, TB, RIGHT>(U, V, X, Y, X2, Y2, S, XT0, VT0, X2T0, K, o);
                         if (TB) *reinterpret_cast<uint4*>(tb_page + (int64_t)tb_rip * T.pitch + (base - st)) = o;
 
                         // exact max bookkeeping (:224-260): H[t] += v[t] - qe ; H[en0] from its left neighbour
@@ -536,14 +566,13 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                 }
                 const int32_t wmax = __reduce_max_sync(FULL, habs);
                 if (lane == 0) sts32(sb + OFF_MH + 4u * (uint32_t)(s3 * NW + warp), (uint32_t)wmax);
-                last_st = st; last_en = en;
                 if (TB && ++tb_rip == T.rows_per_page) {
                     tb_rip = 0; ++tb_pg;
                     if (tb_pg < T.tb_pages) tb_page = C.pool.base + (int64_t)table[tb_pg] * C.pool.page_bytes;
-                    if (tb_lazy) {         // one page ahead: the CTA reads table[tb_pg + 1] a whole page of antidiagonals from now
-                        StallWatch watch;
-                        while (tb_held < T.tb_pages && tb_held < tb_pg + 2)
-                            if (!pool_lazy_grab(C.pool, C.slot_base + (int)blockIdx.x, table, tb_held)) { __nanosleep(4000); watch.poll(C.pool); }
+                    // (thread 0 of a lazily growing task) one page ahead: the CTA reads table[tb_pg + 1] a whole page of antidiagonals from now
+                    if (tid == 0 && tb_pg + 1 < T.tb_pages) {
+                        const int held = (int)lds32(sb + OFF_HELD);
+                        if (held < tb_pg + 2) sts32(sb + OFF_HELD, (uint32_t)pool_lazy_grow(C.pool, C.slot_base + (int)blockIdx.x, table, held, tb_pg + 2));
                     }
                 }
             }
@@ -557,7 +586,11 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
         __syncthreads();             // every traceback row is written
         if (warp == 0) finish_task(C, T, table, ez, cells, TB);
         __syncthreads();
-        if (tid == 0) { pool_free(C.pool, tb_held, table, tb_lazy ? C.slot_base + (int)blockIdx.x : -1); if (C.timeline) C.timeline[2 * T.orig + 1] = global_ns(); }
+        if (tid == 0) {
+            const bool lazy = C.pool.lazy && C.pool.lazy_min_pages > 0 && T.tb_pages >= C.pool.lazy_min_pages;      // as task_pages decided
+            pool_free(C.pool, (int)lds32(sb + OFF_HELD), table, lazy ? C.slot_base + (int)blockIdx.x : -1);
+            if (C.timeline) C.timeline[2 * T.orig + 1] = global_ns();
+        }
     }
 }
 
@@ -582,7 +615,7 @@ inline bool dpx_supports(const DevScoring& sc, const DevTask& t, bool has_wild)
 {
     (void)has_wild;            // wildcard bases: one extra bit per lane in the kernel (T.wild)
     if (t.kind != 1) return false;
-    if (t.flag & (FSV_EZ_GENERIC_SC | FSV_EZ_RIGHT | FSV_EZ_APPROX_MAX | FSV_EZ_APPROX_DROP)) return false;
+    if (t.flag & (FSV_EZ_GENERIC_SC | FSV_EZ_APPROX_MAX | FSV_EZ_APPROX_DROP)) return false;
     if (sc.m != 5) return false;
     return dpx_class_of(dpx_warps_needed(t)) != 0;
 }
@@ -590,25 +623,27 @@ inline bool dpx_supports(const DevScoring& sc, const DevTask& t, bool has_wild)
 constexpr int DPX_EXCL_SMEM = 226 * 1024;   // dynamic shared memory reserved by an exclusive CTA: nothing else fits on its SM
 
 // CTAs to launch for n_tasks tasks of the NW-warp class (persistent CTAs)
-template <bool DUAL, bool TB, int NW>
+template <bool DUAL, int TBM, int NW>
 inline int dpx_grid_one(int sm_count, int n_tasks)
 {
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fsv_fill_dpx_kernel<DUAL, TB, NW, false>, NW * 32, 0) != cudaSuccess) { cudaGetLastError(); per_sm = 1; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fsv_fill_dpx_kernel<DUAL, TBM, NW, false>, NW * 32, 0) != cudaSuccess) { cudaGetLastError(); per_sm = 1; }
     if (per_sm < 1) per_sm = 1;
     return std::max(1, std::min(n_tasks, sm_count * per_sm));
 }
 
-template <bool DUAL, bool TB, int NW>
+template <bool DUAL, int TBM, int NW>
 inline int dpx_launch_one(cudaStream_t stream, int grid, bool excl, const DpxParams& P, std::string* err)
 {
     cudaError_t e = cudaSuccess;
+    DpxParams PK = P;
+    PK.K = DpxConst<DUAL, TBM == 2>(P.C.sc);
     if (excl && NW >= 6) {
-        auto kern = fsv_fill_dpx_kernel<DUAL, TB, (NW >= 6 ? NW : 6), true>;
+        auto kern = fsv_fill_dpx_kernel<DUAL, TBM, (NW >= 6 ? NW : 6), true>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DPX_EXCL_SMEM);
-        if (e == cudaSuccess) kern<<<grid, NW * 32, DPX_EXCL_SMEM, stream>>>(P);
+        if (e == cudaSuccess) kern<<<grid, NW * 32, DPX_EXCL_SMEM, stream>>>(PK);
     } else {
-        fsv_fill_dpx_kernel<DUAL, TB, NW, false><<<grid, NW * 32, 0, stream>>>(P);
+        fsv_fill_dpx_kernel<DUAL, TBM, NW, false><<<grid, NW * 32, 0, stream>>>(PK);
     }
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { if (err) *err = cudaGetErrorString(e); cudaGetLastError(); return FSV_ERR_CUDA; }
@@ -624,33 +659,40 @@ inline int dpx_launch_one(cudaStream_t stream, int grid, bool excl, const DpxPar
         case 8: return CALL(8);                                                   \
     }
 
-template <bool DUAL, bool TB>
+template <bool DUAL, int TBM>
 inline int dpx_grid_nw(int sm_count, int nw, int n_tasks)
 {
-#define FSV_G(N) dpx_grid_one<DUAL, TB, N>(sm_count, n_tasks)
+#define FSV_G(N) dpx_grid_one<DUAL, TBM, N>(sm_count, n_tasks)
     FSV_DPX_DISPATCH(FSV_G)
 #undef FSV_G
     return 1;
 }
-template <bool DUAL, bool TB>
+template <bool DUAL, int TBM>
 inline int dpx_launch_nw(cudaStream_t stream, int nw, int grid, bool excl, const DpxParams& P, std::string* err)
 {
-#define FSV_L(N) dpx_launch_one<DUAL, TB, N>(stream, grid, excl, P, err)
+#define FSV_L(N) dpx_launch_one<DUAL, TBM, N>(stream, grid, excl, P, err)
     FSV_DPX_DISPATCH(FSV_L)
 #undef FSV_L
     return FSV_ERR_INVALID;
 }
 
-// one launch per (warps-per-task class, with/without traceback, exclusive or not)
-inline int dpx_grid(int sm_count, bool dual, bool with_tb, int nw, int n_tasks)
+// One launch per (warps-per-task class, traceback mode 0/1/2, exclusive or not).  The six (DUAL, TBM) families
+// are compiled in separate translation units (fsv_dpx_variant.cu, built in parallel); this is what they export.
+#define FSV_DPX_FAMILY(D, T)                                                                                           \
+    int dpx_grid_##D##T(int sm_count, int nw, int n_tasks);                                                           \
+    int dpx_launch_##D##T(cudaStream_t stream, int nw, int grid, bool excl, const DpxParams& P, std::string* err);
+FSV_DPX_FAMILY(0, 0) FSV_DPX_FAMILY(0, 1) FSV_DPX_FAMILY(0, 2) FSV_DPX_FAMILY(1, 0) FSV_DPX_FAMILY(1, 1) FSV_DPX_FAMILY(1, 2)
+#undef FSV_DPX_FAMILY
+
+inline int dpx_grid(int sm_count, bool dual, int tbm, int nw, int n_tasks)
 {
-    if (dual) return with_tb ? dpx_grid_nw<true, true>(sm_count, nw, n_tasks) : dpx_grid_nw<true, false>(sm_count, nw, n_tasks);
-    return with_tb ? dpx_grid_nw<false, true>(sm_count, nw, n_tasks) : dpx_grid_nw<false, false>(sm_count, nw, n_tasks);
+    if (dual) return tbm == 2 ? dpx_grid_12(sm_count, nw, n_tasks) : tbm ? dpx_grid_11(sm_count, nw, n_tasks) : dpx_grid_10(sm_count, nw, n_tasks);
+    return tbm == 2 ? dpx_grid_02(sm_count, nw, n_tasks) : tbm ? dpx_grid_01(sm_count, nw, n_tasks) : dpx_grid_00(sm_count, nw, n_tasks);
 }
-inline int dpx_launch(cudaStream_t stream, bool dual, bool with_tb, int nw, int grid, bool excl, const DpxParams& P, std::string* err)
+inline int dpx_launch(cudaStream_t stream, bool dual, int tbm, int nw, int grid, bool excl, const DpxParams& P, std::string* err)
 {
-    if (dual) return with_tb ? dpx_launch_nw<true, true>(stream, nw, grid, excl, P, err) : dpx_launch_nw<true, false>(stream, nw, grid, excl, P, err);
-    return with_tb ? dpx_launch_nw<false, true>(stream, nw, grid, excl, P, err) : dpx_launch_nw<false, false>(stream, nw, grid, excl, P, err);
+    if (dual) return tbm == 2 ? dpx_launch_12(stream, nw, grid, excl, P, err) : tbm ? dpx_launch_11(stream, nw, grid, excl, P, err) : dpx_launch_10(stream, nw, grid, excl, P, err);
+    return tbm == 2 ? dpx_launch_02(stream, nw, grid, excl, P, err) : tbm ? dpx_launch_01(stream, nw, grid, excl, P, err) : dpx_launch_00(stream, nw, grid, excl, P, err);
 }
 
 }  // namespace fsv

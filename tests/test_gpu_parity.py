@@ -274,6 +274,35 @@ def test_wildcard_bases_on_the_dpx_kernel(oracle, aligner, preset, w):
     assert aligner.stats()["exact_path_tasks"] == before
 
 
+@pytest.mark.parametrize("preset,w", [("asm5", 3001), ("hifiasm", 500), ("map-hifi", 751)])
+def test_right_aligned_gaps_on_the_dpx_kernel(oracle, aligner, preset, w):
+    """KSW_EZ_RIGHT (ties go to the later state, continuation bits on >= 0; ksw2_extz2_sse.c:197-222) as minimap2's
+    left extension uses it (RIGHT | REV_CIGAR | EXTZ_ONLY), on repeats where left and right placement differ."""
+    rng = np.random.default_rng(99 + w)
+    pairs = []
+    for L in (900, 2300, 4000, 6100):
+        unit = synth.random_seq(rng, int(rng.integers(2, 9)))
+        ref = synth.random_seq(rng, L).copy()
+        for _ in range(6):                                   # tandem repeats: a gap can slide inside them
+            k = int(rng.integers(0, L - 200)); n = int(rng.integers(20, 120))
+            ref[k:k + n] = np.resize(unit, n)
+        q = synth.mutate(rng, ref, 0.004, 0.01, 0.01)
+        pairs.append((q, ref))
+    flags = np.array([_abi.EZ_RIGHT, _abi.EZ_RIGHT | _abi.EZ_REV_CIGAR | _abi.EZ_EXTZ_ONLY, _abi.EZ_RIGHT | _abi.EZ_EXTZ_ONLY,
+                      _abi.EZ_RIGHT | _abi.EZ_REV_CIGAR], dtype=np.int32)
+    from focalsv_b200.presets import PRESETS
+    g = synth._pack("right." + preset, preset, pairs, w, PRESETS[preset].zdrop, flags=flags)
+    before = aligner.stats()["exact_path_tasks"]
+    bad, ores, gres = compare_group(oracle, aligner, g)
+    assert not bad, bad
+    assert aligner.stats()["exact_path_tasks"] == before
+    # and the placement really differs from the left-aligned run for at least one task
+    g2 = g._replace(tasks=g.tasks.copy()); g2.tasks["flag"] &= ~_abi.EZ_RIGHT
+    res_l, cig_l = aligner.align_batch(g2.scoring, g2.qarena, g2.tarena, g2.tasks)
+    res_r, cig_r = aligner.align_batch(g.scoring, g.qarena, g.tarena, g.tasks)
+    assert any(not np.array_equal(task_cigar(res_l[i], cig_l), task_cigar(res_r[i], cig_r)) for i in range(len(res_l)))
+
+
 def test_mixed_kernel_variants_share_the_pool(oracle, aligner):
     """One batch whose tasks land on several kernel variants at once (1/2/4-warp DPX classes, score-only and
     CIGAR, wildcard tasks, and right-aligned tasks on the general kernel), all running concurrently on one page pool."""
