@@ -22,6 +22,7 @@
 // wider than 8 warps of vectors) go to the general kernel in fsv_fill_exact.cuh.
 #pragma once
 #include <string>
+#include <type_traits>
 
 #include "fsv_backtrack.cuh"
 #include "fsv_common.cuh"
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
         int Vt = tid - NT;          // forces the (re)arm path on the first antidiagonal
         uint32_t tw = 0, qw = 0;
         uint32_t amb = 0;           // wildcard bases of the two windows, one bit per lane: target << 16 | query (tasks with T.wild only)
-        const bool wild = T.wild != 0;
+        const bool wild_task = T.wild != 0;
         uint32_t qpre = 0; int qpre_r = -1;     // query base the lowest vector of the band needs at antidiagonal qpre_r
         EzState ez; ez.reset();     // complete only in warp 0 (the bookkeeping warp)
         int64_t cells = 0;
@@ -294,6 +295,10 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
         int32_t habs_p = INT32_MIN; bool act_p = false; int st0p = 0, en0p = 0;   // this thread at r-1
         int s3 = 0;                 // r % 3
 
+        // The antidiagonal loop exists twice, with and without the wildcard bookkeeping, chosen once per task:
+        // left to itself the compiler predicates the `if (wild)` blocks, and predicated-off instructions still issue.
+        auto fill_loop = [&](auto wild_c) {
+        constexpr bool wild = decltype(wild_c)::value;
         for (int r = 0;; ++r) {
             const int par = r & 1, ppar = par ^ 1;
             const int s3m1 = s3 == 0 ? 2 : s3 - 1, s3m2 = s3 == 2 ? 0 : s3 + 1;   // (r-1)%3, (r-2)%3
@@ -581,6 +586,8 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
             M2 = M1; nt2 = nt1;
             s3 = s3 == 2 ? 0 : s3 + 1;
         }
+        };
+        if (wild_task) fill_loop(std::true_type{}); else fill_loop(std::false_type{});
         if (!dropped && stop_r < n_diag) ez.zdropped = 1;      // band exhausted (:111-114)
 
         __syncthreads();             // every traceback row is written

@@ -392,6 +392,9 @@ int fsvo_extz2(int qlen, const uint8_t* query, int tlen, const uint8_t* target, 
  * requested; tests/test_oracle_fast_path.py checks it lane for lane against the scalar loop. */
 typedef int8_t i8;
 #define SMAX(a, b) ((a) > (b) ? (a) : (b))
+/* two clones: the AVX2 one (32 lanes) is picked at load time on hosts that have it, so the CPU arm of the
+ * bench is at least as wide as the reference's 16-lane SSE build */
+__attribute__((target_clones("avx2", "default")))
 static void extd2_row_fast(int n, i8* restrict u, i8* restrict v, i8* restrict x, i8* restrict y, i8* restrict x2,
                            i8* restrict y2, const i8* restrict s, uint8_t* restrict pr, i8 x1, i8 x21, i8 v1,
                            i8 q_, i8 q2_, i8 qe_, i8 qe2_, i8 mch, int mode,
