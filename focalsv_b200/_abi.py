@@ -1,4 +1,4 @@
-"""ctypes / numpy mirrors of include/focalsv_cuda.h (ABI version 1).
+"""ctypes / numpy mirrors of include/focalsv_cuda.h (ABI version 2).
 
 Kept in one place so that the product binding (focalsv_b200.api), the oracle
 wrapper (oracle/oracle.py) and the tests all see the same layouts.
@@ -7,7 +7,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 NEG_INF = -0x40000000
 
 # ksw2.h:8-14
@@ -40,7 +40,9 @@ RESULT_DTYPE = np.dtype([("max", "<i4"), ("zdropped", "<i4"), ("max_q", "<i4"), 
                          ("mqe", "<i4"), ("mqe_t", "<i4"), ("mte", "<i4"), ("mte_q", "<i4"),
                          ("score", "<i4"), ("reach_end", "<i4"), ("n_cigar", "<i4"), ("status", "<i4"),
                          ("cigar_off", "<i8"), ("cells", "<i8")], align=True)
-assert TASK_DTYPE.itemsize == 40 and RESULT_DTYPE.itemsize == 64
+SIGNATURE_DTYPE = np.dtype([("task", "<i4"), ("svtype", "<i4"), ("pos", "<i8"), ("svlen", "<i4"), ("read_start", "<i4"),
+                            ("read_end", "<i4"), ("pad_", "<i4")], align=True)
+assert TASK_DTYPE.itemsize == 40 and RESULT_DTYPE.itemsize == 64 and SIGNATURE_DTYPE.itemsize == 32
 
 # fields that must be bit-identical to ksw_extz_t (ksw2.h:23-32)
 EZ_FIELDS = ("max", "zdropped", "max_q", "max_t", "mqe", "mqe_t", "mte", "mte_q", "score", "reach_end", "n_cigar")

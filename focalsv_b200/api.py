@@ -20,7 +20,7 @@ LIB_PATH = os.environ.get("FSV_LIB_PATH") or os.path.join(_HERE, "libfocalsv_cud
 EXPORTS = ("fsv_init", "fsv_destroy", "fsv_strerror", "fsv_last_error", "fsv_abi_version", "fsv_device_count",
            "fsv_get_stats", "fsv_set_option", "fsv_align_batch", "fsv_batch_create", "fsv_batch_run",
            "fsv_batch_fetch", "fsv_batch_destroy", "fsv_ksw_extz2", "fsv_ksw_extd2", "fsv_task_cells",
-           "fsv_lpt_bins", "fsv_measure_int_peak", "fsv_batch_timeline")
+           "fsv_lpt_bins", "fsv_measure_int_peak", "fsv_batch_timeline", "fsv_batch_signatures")
 
 _lib = None
 
@@ -57,6 +57,7 @@ def load_library(path=None):
     lib.fsv_batch_fetch.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
     lib.fsv_batch_destroy.argtypes = [vp]
     lib.fsv_batch_timeline.argtypes = [vp, vp]
+    lib.fsv_batch_signatures.argtypes = [vp, vp, C.c_int, vp, sz, C.POINTER(sz)]
     lib.fsv_batch_destroy.restype = None
     lib.fsv_task_cells.argtypes = [i32, i32, i32]
     lib.fsv_task_cells.restype = i64
@@ -217,6 +218,26 @@ class Batch(object):
         rc = self._lib.fsv_batch_fetch(self._h, out.ctypes.data, cig.ctypes.data, int(cigar_cap), C.byref(used))
         self._al._check(rc, "fsv_batch_fetch")
         return out, cig[:used.value]
+
+    def signatures(self, ref_start=None, min_svlen=30):
+        """DEL / INS signatures of every task, extracted on the device from the CIGARs of the last run
+        (extract_contig_signature_CCS.py:14-127); only these records are copied back.  `ref_start[i]` is the
+        reference coordinate of target[0] of task i.  Returns a SIGNATURE_DTYPE array (per task: DELs, then INSs)."""
+        n = len(self.tasks)
+        rs = None if ref_start is None else np.ascontiguousarray(ref_start, dtype=np.int64)
+        if rs is not None and len(rs) != n:
+            raise ValueError("ref_start must have one entry per task")
+        cap = 1024
+        while True:
+            out = np.zeros(cap, dtype=_abi.SIGNATURE_DTYPE)
+            used = C.c_size_t(0)
+            rc = self._lib.fsv_batch_signatures(self._h, None if rs is None else rs.ctypes.data, int(min_svlen),
+                                                out.ctypes.data, cap, C.byref(used))
+            if rc == _abi.ERR_CIGAR_CAP:
+                cap = int(used.value) + 16
+                continue
+            self._al._check(rc, "fsv_batch_signatures")
+            return out[:used.value]
 
     def timeline(self):
         """(n, 2) int64: device start / end time (ns) of every task in the last run."""

@@ -22,6 +22,7 @@
 #include "fsv_fill_dpx.cuh"
 #include "fsv_fill_exact.cuh"
 #include "fsv_peaks.cuh"
+#include "fsv_signatures.cuh"
 
 using namespace fsv;
 
@@ -690,6 +691,56 @@ extern "C" int fsv_batch_fetch(fsv_batch* b, fsv_result* out, uint32_t* cigar, s
         c->stats.d2h_bytes += used * 4;
     }
     return FSV_OK;
+}
+
+extern "C" int fsv_batch_signatures(fsv_batch* b, const int64_t* ref_start, int min_svlen, fsv_signature* out, size_t cap, size_t* n_out)
+{
+    if (!b || !n_out || (cap && !out)) return FSV_ERR_INVALID;
+    fsv_ctx* c = b->ctx;
+    if (b->state != 1) return FSV_ERR_STATE;
+    *n_out = 0;
+    const int n = (int)b->n;
+    if (!n) return FSV_OK;
+    CK(c, cudaSetDevice(c->device));
+    size_t sz_counts = 0, sz_offs = 0, sz_ref = 0, sz_out = 0;
+    int32_t* d_counts = (int32_t*)dev_alloc(c, (size_t)n * 8, &sz_counts);
+    long long* d_offs = (long long*)dev_alloc(c, (size_t)n * 8, &sz_offs);
+    long long* d_ref = ref_start ? (long long*)dev_alloc(c, (size_t)n * 8, &sz_ref) : nullptr;
+    fsv_signature* d_out = nullptr;
+    int rc = FSV_OK;
+    auto done = [&](int code) {
+        dev_release(c, d_counts, sz_counts); dev_release(c, d_offs, sz_offs); dev_release(c, d_ref, sz_ref); dev_release(c, d_out, sz_out);
+        return code;
+    };
+    if (!d_counts || !d_offs || (ref_start && !d_ref)) return done(FSV_ERR_NOMEM);
+#define CKS(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { c->last_error = std::string(#call) + " -> " + cudaGetErrorString(e_); cudaGetLastError(); return done(FSV_ERR_CUDA); } } while (0)
+    if (ref_start) CKS(cudaMemcpyAsync(d_ref, ref_start, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    const int threads = 128, blocks = (n + threads - 1) / threads;
+    fsv_sig_count_kernel<<<blocks, threads, 0, c->stream>>>(b->d_results, b->d_cigar, d_ref, n, min_svlen, d_counts);
+    CKS(cudaGetLastError());
+    std::vector<int32_t> counts((size_t)n * 2);
+    CKS(cudaMemcpyAsync(counts.data(), d_counts, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CKS(cudaStreamSynchronize(c->stream));
+    std::vector<long long> offs((size_t)n);
+    long long total = 0;
+    for (int i = 0; i < n; ++i) { offs[(size_t)i] = total; total += counts[2 * (size_t)i] + counts[2 * (size_t)i + 1]; }
+    *n_out = (size_t)total;
+    c->stats.other_launches += 1;
+    c->stats.d2h_bytes += (int64_t)n * 8;
+    if ((size_t)total > cap) return done(FSV_ERR_CIGAR_CAP);
+    if (total) {
+        d_out = (fsv_signature*)dev_alloc(c, (size_t)total * sizeof(fsv_signature), &sz_out);
+        if (!d_out) return done(FSV_ERR_NOMEM);
+        CKS(cudaMemcpyAsync(d_offs, offs.data(), (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+        fsv_sig_write_kernel<<<blocks, threads, 0, c->stream>>>(b->d_results, b->d_cigar, d_ref, n, min_svlen, d_counts, d_offs, d_out);
+        CKS(cudaGetLastError());
+        CKS(cudaMemcpyAsync(out, d_out, (size_t)total * sizeof(fsv_signature), cudaMemcpyDeviceToHost, c->stream));
+        CKS(cudaStreamSynchronize(c->stream));
+        c->stats.other_launches += 1;
+        c->stats.d2h_bytes += total * (int64_t)sizeof(fsv_signature);
+    }
+#undef CKS
+    return done(rc);
 }
 
 extern "C" int fsv_batch_timeline(fsv_batch* b, int64_t* start_end_ns)

@@ -43,17 +43,17 @@ def cigar_tuples(words):
     return [(int(w) & 0xF, int(w) >> 4) for w in words]
 
 
-def realign_regions(aligner, windows, contigs, preset="asm5", bw=2000, flag=0):
+def realign_regions(aligner, windows, contigs, preset="asm5", bw=2000, flag=0, zdrop=None):
     """Align contig i against window i (same region) on the GPU.
 
     windows: list of (chrom, start, sequence); contigs: list of (qname, sequence).
     Scoring / z-drop are the preset's (presets.py); the band is minimap2's bw*1.5+1 for `-r{bw}`
-    (DipPAV_variant_call.py:103 passes -r2k).  Returns one AlignedContig per pair."""
+    (DipPAV_variant_call.py:103 passes -r2k); `zdrop` overrides the preset's.  Returns one AlignedContig per pair."""
     p = PRESETS[preset]
     sc = scoring_for(preset)
     q = [encode(s) for _, s in contigs]
     t = [encode(s) for _, _, s in windows]
-    tasks = make_tasks([len(x) for x in q], [len(x) for x in t], ksw_band(bw), p.zdrop, 0, flag)
+    tasks = make_tasks([len(x) for x in q], [len(x) for x in t], ksw_band(bw), p.zdrop if zdrop is None else zdrop, 0, flag)
     qa = np.concatenate(q) if q else np.zeros(0, np.uint8)
     ta = np.concatenate(t) if t else np.zeros(0, np.uint8)
     res, arena = aligner.align_batch(sc, qa, ta, tasks)
@@ -120,6 +120,32 @@ def extract_sig_from_cigar(rec, min_svlen=30):
         return a._replace(svlen=b.pos + b.svlen - a.pos, read_end=a.read_start + 1) if ok else None
 
     return _merge_runs(dels, del_rule), _merge_runs(inss, ins_rule), ro, co
+
+
+def realign_regions_signatures(aligner, windows, contigs, preset="asm5", bw=2000, flag=0, min_svlen=30, zdrop=None):
+    """The same alignment as realign_regions, but the CIGARs never leave the GPU: the DEL / INS signatures are
+    extracted on the device (fsv_batch_signatures) and only they come back.  Returns a list of Signature in the
+    order `signatures(realign_regions(...))` gives."""
+    p = PRESETS[preset]
+    sc = scoring_for(preset)
+    q = [encode(s) for _, s in contigs]
+    t = [encode(s) for _, _, s in windows]
+    tasks = make_tasks([len(x) for x in q], [len(x) for x in t], ksw_band(bw), p.zdrop if zdrop is None else zdrop, 0, flag)
+    qa = np.concatenate(q) if q else np.zeros(0, np.uint8)
+    ta = np.concatenate(t) if t else np.zeros(0, np.uint8)
+    b = aligner.batch(sc, qa, ta, tasks)
+    try:
+        b.run()
+        sig = b.signatures(np.array([int(s) for _, s, _ in windows], dtype=np.int64), min_svlen)
+    finally:
+        b.close()
+    out = []
+    for r in sig:
+        chrom = windows[int(r["task"])][0]
+        qname = contigs[int(r["task"])][0]
+        out.append(Signature(chrom, "INS" if int(r["svtype"]) else "DEL", int(r["pos"]), int(r["svlen"]), qname,
+                             int(r["read_start"]), int(r["read_end"]), "+", "cigar", 60))
+    return out
 
 
 def signatures(records, min_svlen=30):

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define FSV_ABI_VERSION 1
+#define FSV_ABI_VERSION 2
 
 /* ksw2.h:6 */
 #define FSV_NEG_INF (-0x40000000)
@@ -160,6 +160,25 @@ void fsv_batch_destroy(fsv_batch* batch);
 /* Per-task device timeline of the last run (GPU globaltimer, ns): start_end_ns[2*i] = when task i got its
  * traceback pages and started, [2*i+1] = when its CIGAR was written.  For schedule analysis / tracing. */
 int fsv_batch_timeline(fsv_batch* batch, int64_t* start_end_ns);
+
+/* ---- next row: CIGAR -> DEL / INS signatures on the device -------------
+ * What the reference does with every aligned contig right after the alignment
+ * (focalsv/4_sv_calling/Dippav/extract_contig_signature_CCS.py:14-127, extract_sig_from_cigar): keep D / I
+ * operations >= min_svlen and fold neighbouring ones of the same contig (:49-127).  Runs on the CIGARs of a batch
+ * that has been run (fsv_batch_run) while they are still in HBM; only the signatures are copied back.
+ * ref_start[i] = reference coordinate of target[0] of task i (NULL = 0).  Per task: its DELs, then its INSs, in
+ * CIGAR order.  On a too-small `out` returns FSV_ERR_CIGAR_CAP with *n_out = records needed. */
+typedef struct fsv_signature {
+    int32_t task;             /* index in the caller's task array */
+    int32_t svtype;           /* 0 = DEL, 1 = INS */
+    int64_t pos;              /* reference offset (sig[2]) */
+    int32_t svlen;            /* sig[3] */
+    int32_t read_start;       /* contig offsets (sig[5], sig[6]) */
+    int32_t read_end;
+    int32_t pad_;
+} fsv_signature;
+int fsv_batch_signatures(fsv_batch* batch, const int64_t* ref_start, int min_svlen,
+                         fsv_signature* out, size_t cap, size_t* n_out);
 
 /* ---- single-task convenience, argument-for-argument ksw2.h:54-61 ------
  * (km dropped; ez -> fsv_result + caller-owned cigar buffer). */

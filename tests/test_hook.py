@@ -63,3 +63,70 @@ def test_gpu_region_call_gives_identical_records_and_signatures(oracle, aligner)
     got = hook.realign_regions(aligner, windows, contigs, preset="asm5", bw=2000)
     assert got == want
     assert hook.signatures(got) == hook.signatures(want)
+
+
+def test_signature_rules_match_the_references_own_function():
+    """tests/golden/sig_golden.json holds inputs and outputs of the reference's own extract_sig_from_cigar
+    (extract_contig_signature_CCS.py:14-127, run by tests/golden/make_sig_golden.py): clips, adjacent I/D,
+    every merge rule."""
+    import json, os
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sig_golden.json")))
+    assert len(g["cases"]) >= 100
+    merged = 0
+    for c in g["cases"]:
+        r = c["record"]
+        rec = hook.AlignedContig(r["qname"], r["reference_name"], r["pos"], 0, [tuple(x) for x in r["cigar"]],
+                                 r["is_reverse"], r["mapq"], 0, 0, False)
+        d, i, ro, co = hook.extract_sig_from_cigar(rec, c["min_svlen"])
+        assert [list(x) for x in d] == c["dels"] and [list(x) for x in i] == c["inss"]
+        assert (ro, co) == (c["ref_end"], c["contig_end"])
+        n_raw = sum(1 for op, n in rec.cigar if op in (1, 2) and n >= c["min_svlen"])
+        merged += n_raw - len(d) - len(i)
+    assert merged > 20          # the merge rules were exercised
+
+
+def _close_sv_regions(seed, n=5):
+    """Contigs whose planted events sit close together, so that the per-contig merge rules fire."""
+    rng = np.random.default_rng(seed)
+    windows, contigs = [], []
+    for i in range(n):
+        ref = synth.random_seq(rng, 9000 + 700 * i)
+        k = 3000
+        if i % 2 == 0:      # two long insertions 60 bp apart, then a deletion
+            q = np.concatenate([ref[:k], synth.random_seq(rng, 400), ref[k:k + 60], synth.random_seq(rng, 350), ref[k + 60:6000], ref[6300:]])
+        else:               # two long deletions whose starts are 100 bp apart
+            q = np.concatenate([ref[:k], ref[k + 200:k + 300], ref[k + 500:]])
+        q = synth.mutate(rng, q, 0.0005, 0.0002, 0.0002)
+        windows.append(("chr%d" % (1 + i), 5000000 + 31337 * i, ref)); contigs.append(("contig_hp2_%d" % i, q))
+    return windows, contigs
+
+
+@pytest.mark.gpu
+def test_device_signatures_equal_the_host_rules(aligner):
+    """fsv_batch_signatures (CIGARs stay in HBM) against extract_sig_from_cigar on the fetched CIGARs."""
+    # z-drop 2000: with asm5's 200 two large events this close end the alignment (minimap2 would re-chain there)
+    for windows, contigs in (_regions(8, n=6)[:2], _close_sv_regions(9)):
+        recs = hook.realign_regions(aligner, windows, contigs, preset="asm5", bw=2000, zdrop=2000)
+        for min_svlen in (30, 50):
+            want = hook.signatures(recs, min_svlen)
+            got = hook.realign_regions_signatures(aligner, windows, contigs, preset="asm5", bw=2000, min_svlen=min_svlen, zdrop=2000)
+            assert got == want
+            assert len(want) >= len(windows)
+    # the second set really merged something: fewer signatures than qualifying CIGAR operations
+    raw = sum(1 for r in recs for op, n in r.cigar if op in (1, 2) and n >= 30)
+    assert len(hook.signatures(recs, 30)) < raw
+
+
+@pytest.mark.gpu
+def test_device_signatures_empty_and_capacity(aligner):
+    from focalsv_b200.presets import scoring_for as sf
+    from focalsv_b200.api import make_tasks
+    seq = synth.random_seq(np.random.default_rng(1), 500)
+    b = aligner.batch(sf("asm5"), seq, seq, make_tasks([500], [500], 100, 200))
+    try:
+        with pytest.raises(Exception):
+            b.signatures()                      # not run yet: FSV_ERR_STATE
+        b.run()
+        assert len(b.signatures(np.array([7], dtype=np.int64))) == 0      # identical sequences: no signature
+    finally:
+        b.close()
