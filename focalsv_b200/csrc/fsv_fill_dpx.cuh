@@ -242,10 +242,15 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
     constexpr uint32_t OFF_EDGE = 0, OFF_MH = 2 * NW * 32, OFF_KEY = OFF_MH + 3 * NW * 4, OFF_HEN0 = OFF_KEY + 12,
                        OFF_HST0 = OFF_HEN0 + 12, OFF_STOP = OFF_HST0 + 12, OFF_TASK = OFF_STOP + 4, OFF_HELD = OFF_TASK + 4, SH_BYTES = OFF_HELD + 4;
     __shared__ __align__(16) uint32_t sh_raw[(SH_BYTES + 15) / 16 * 4];
-    const uint32_t sb = (uint32_t)__cvta_generic_to_shared(sh_raw);
+    uint32_t sb = (uint32_t)__cvta_generic_to_shared(sh_raw);
     const RunCtx& C = P.C;
     const DevScoring& sc = C.sc;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifndef FSV_NO_OPAQUE
+    // opaque to the compiler: otherwise it rebuilds these from S2R / the shared window base inside the fill loop
+    // (10+ instructions per antidiagonal) instead of keeping four registers
+    asm volatile("" : "+r"(tid), "+r"(lane), "+r"(warp), "+r"(sb));
+#endif
     const unsigned FULL = 0xffffffffu;
     const DpxK& K = P.K;
     const uint32_t extSel = DUAL ? 0xB391u : 0x4341u;                  // int8 (signed / unsigned) -> int16
