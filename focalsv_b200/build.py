@@ -2,7 +2,7 @@
 
 The shared object lands next to this file (focalsv_b200/libfocalsv_cuda.so): it is
 git-ignored but travels to the GPU box with the gpurun snapshot.  The DPX fill kernel is
-compiled as six translation units (dual x traceback mode), in parallel, then linked with the
+compiled as eight translation units (dual x traceback/approx mode), in parallel, then linked with the
 C ABI (fsv_capi.cu).
 """
 import os
@@ -18,7 +18,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CFLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
           "-Xcompiler", "-fPIC,-O3,-Wall", "--use_fast_math", "-Xptxas", "-v",
           "-I", os.path.join(HERE, "..", "include")]
-VARIANTS = [(d, t) for d in (0, 1) for t in (0, 1, 2)]
+VARIANTS = [(d, t) for d in (0, 1) for t in (0, 1, 2, 3)]
 
 
 def sources():

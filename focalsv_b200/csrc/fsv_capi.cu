@@ -496,7 +496,7 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
             const int ti = ord[k];
             const DevTask& d = b->tasks[ti];
             if (kind == 0) { if (b->is_dpx[ti]) continue; }
-            else if (!b->is_dpx[ti] || d.nw != nw || ((d.flag & FSV_EZ_SCORE_ONLY) ? 0 : (d.flag & FSV_EZ_RIGHT) ? 2 : 1) != with_tb || (int)is_excl[ti] != excl) continue;
+            else if (!b->is_dpx[ti] || d.nw != nw || ((d.flag & FSV_EZ_SCORE_ONLY) ? ((d.flag & FSV_EZ_APPROX_MAX) ? 3 : 0) : (d.flag & FSV_EZ_RIGHT) ? 2 : 1) != with_tb || (int)is_excl[ti] != excl) continue;
             b->work.push_back(ti);
             if (kind == 0 && d.kind == 1 && d.pitch + 96 > c->exact_smem_lanes) ws_need = std::max<int64_t>(ws_need, d.pitch + 96);
         }
@@ -508,8 +508,8 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
         b->launches.push_back(L);
     };
     static const int kClasses[5] = {8, 6, 4, 2, 1};
-    for (int cls : {8, 6}) for (int with_tb = 2; with_tb >= 0; --with_tb) add_launch(1, cls, with_tb, 1);
-    for (int cls : kClasses) for (int with_tb = 2; with_tb >= 0; --with_tb) add_launch(1, cls, with_tb, 0);
+    for (int cls : {8, 6}) for (int with_tb = 3; with_tb >= 0; --with_tb) add_launch(1, cls, with_tb, 1);
+    for (int cls : kClasses) for (int with_tb = 3; with_tb >= 0; --with_tb) add_launch(1, cls, with_tb, 0);
     add_launch(0, 0, 0, 0);
     tr.lap("create: sort + work lists");
     b->ws_lanes = ws_need ? pow2_at_least(ws_need) : 0;

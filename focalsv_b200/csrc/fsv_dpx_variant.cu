@@ -1,5 +1,5 @@
 // fsv_dpx_variant.cu — one (DUAL, TBM) family of the DPX fill kernel per translation unit.
-// Compiled six times by focalsv_b200/build.py with -DFSV_VARIANT_DUAL=0|1 -DFSV_VARIANT_TBM=0|1|2 (in parallel:
+// Compiled eight times by focalsv_b200/build.py with -DFSV_VARIANT_DUAL=0|1 -DFSV_VARIANT_TBM=0|1|2|3 (in parallel:
 // the kernel is large and ptxas time is what the build waits for).
 #include <algorithm>
 #include <string>
@@ -7,7 +7,7 @@
 #include "fsv_fill_dpx.cuh"
 
 #ifndef FSV_VARIANT_DUAL
-#error "compile with -DFSV_VARIANT_DUAL=0|1 -DFSV_VARIANT_TBM=0|1|2"
+#error "compile with -DFSV_VARIANT_DUAL=0|1 -DFSV_VARIANT_TBM=0|1|2|3"
 #endif
 
 #define FSV_CAT3_(a, b, c) a##b##c

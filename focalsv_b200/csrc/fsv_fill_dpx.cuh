@@ -228,19 +228,21 @@ __device__ __forceinline__ void dpx_cells(uint32_t (&U)[8], uint32_t (&V)[8], ui
 
 // EXCL only tags a second copy of the 6- and 8-warp kernels: it is launched with (almost) all of an SM's
 // shared memory reserved, so that a CTA working on one of the few very long tasks has its SM to itself.
-// TBM: 0 = score only, 1 = traceback, ties to the left (default), 2 = traceback, ties to the right (KSW_EZ_RIGHT).
+// TBM: 0 = score only, 1 = traceback, ties to the left (default), 2 = traceback, ties to the right (KSW_EZ_RIGHT),
+// 3 = score only with KSW_EZ_APPROX_MAX (:270-286): no H[] at all, one cell is followed greedily.
 template <bool DUAL, int TBM, int NW, bool EXCL = false>
 __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kernel(const __grid_constant__ DpxParams P)
 {
     constexpr int NT = NW * 32;
-    constexpr bool TB = TBM != 0, RIGHT = TBM == 2;
+    constexpr bool TB = TBM == 1 || TBM == 2, RIGHT = TBM == 2, APPROX = TBM == 3;
     using KC = DpxConst<DUAL, RIGHT>;
     // one shared block, addressed from a single base register:
     //   edge slots [2 parities][NW] x 32 B : {x, v, x2, qw} of lane 15 of each warp's last vector, then its H and wildcard bit
     //   per-warp max H, ring over 3 antidiagonals; tie key / H[en0] / H[st0] rings; stop flag; task index;
-    //   traceback pages the task holds (thread 0's; fewer than tb_pages = a lazily growing task)
+    //   traceback pages the task holds (thread 0's; fewer than tb_pages = a lazily growing task);
+    //   APPROX: v[t*] and u[t*+1] of the followed cell, by antidiagonal parity
     constexpr uint32_t OFF_EDGE = 0, OFF_MH = 2 * NW * 32, OFF_KEY = OFF_MH + 3 * NW * 4, OFF_HEN0 = OFF_KEY + 12,
-                       OFF_HST0 = OFF_HEN0 + 12, OFF_STOP = OFF_HST0 + 12, OFF_TASK = OFF_STOP + 4, OFF_HELD = OFF_TASK + 4, SH_BYTES = OFF_HELD + 4;
+                       OFF_HST0 = OFF_HEN0 + 12, OFF_STOP = OFF_HST0 + 12, OFF_TASK = OFF_STOP + 4, OFF_HELD = OFF_TASK + 4, OFF_APV = OFF_HELD + 4, OFF_APU = OFF_APV + 8, SH_BYTES = OFF_APU + 8;
     __shared__ __align__(16) uint32_t sh_raw[(SH_BYTES + 15) / 16 * 4];
     uint32_t sb = (uint32_t)__cvta_generic_to_shared(sh_raw);
     const RunCtx& C = P.C;
@@ -298,6 +300,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
         int32_t M1 = 0, M2 = 0;     // max H of antidiagonals r-1, r-2
         bool nt1 = false, nt2 = false;   // was the argmax of r-1 / r-2 needed?
         int32_t habs_p = INT32_MIN; bool act_p = false; int st0p = 0, en0p = 0;   // this thread at r-1
+        int32_t H0 = 0; int ap_t = 0;   // APPROX: score and column of the one cell that is followed (last_H0_t, :271-283); every thread keeps them
         int s3 = 0;                 // r % 3
 
         // The antidiagonal loop exists twice, with and without the wildcard bookkeeping, chosen once per task:
@@ -329,8 +332,30 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                 nbX = e.x; nbV = e.y; nbX2 = e.z; nbQ = e.w;
             }
 
+            if (APPROX) {
+                // ---- approximate maximum (:270-286): antidiagonal d = r-1 posted v[t*] and u[t*+1] behind the last
+                // barrier; every thread does the same scalar update, so all of them leave the loop together
+                if (r >= 1) {
+                    const int d = r - 1;
+                    if (d >= stop_r) break;                                   // band exhausted (:111)
+                    int st0d, en0d;
+                    band_limits(d, qlen, tlen, w, st0d, en0d);
+                    cells += en0d - st0d + 1;
+                    const int32_t pv = (int32_t)lds32(sb + OFF_APV + 4u * (uint32_t)ppar), pu = (int32_t)lds32(sb + OFF_APU + 4u * (uint32_t)ppar);
+                    if (d == 0) { H0 = pv + K.bias - K.r0_bias; ap_t = 0; }
+                    else {
+                        const bool in0 = ap_t >= st0d && ap_t <= en0d, in1 = ap_t + 1 >= st0d && ap_t + 1 <= en0d;
+                        if (in0 && in1) { if (pv > pu) H0 += pv; else { H0 += pu; ++ap_t; } }
+                        else if (in0) H0 += pv;
+                        else { ++ap_t; H0 += pu; }
+                    }
+                    // extz2 tests the z-drop from the second antidiagonal on (:283 sits inside `if (r > 0)`), the dual variant on every one
+                    if ((T.flag & FSV_EZ_APPROX_DROP) && (DUAL || d > 0) && ez.apply_zdrop(H0, d, ap_t, T.zdrop, sc.e_drop)) { dropped = true; break; }
+                    if (d == n_diag - 1) { if (en0d == tlen - 1) ez.score = H0; break; }
+                }
+            }
             // ---- (A) antidiagonal d = r-2 is final: bookkeeping (ksw2_extz2_sse.c:262-269)
-            if (r >= 2) {
+            if (!APPROX && r >= 2) {
                 if ((int)lds32(sb + OFF_STOP) < r) { dropped = true; break; }      // set during an EARLIER iteration: every thread agrees
                 maxrun = max(maxrun, M2);
                 const int d = r - 2;
@@ -362,7 +387,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                 }
             }
             // ---- (B) antidiagonal r-1: its maximum, and (only if observable, ksw2.h:164-174) who holds it
-            if (r >= 1 && r - 1 < stop_r) {
+            if (!APPROX && r >= 1 && r - 1 < stop_r) {
                 const int32_t m = __reduce_max_sync(FULL, lane < NW ? (int32_t)lds32(sb + OFF_MH + 4u * (uint32_t)(s3m1 * NW + lane)) : INT32_MIN);
                 M1 = m;
                 const int32_t mr = max(maxrun, M2);      // ez.max once r-2 is accounted for
@@ -394,11 +419,18 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                     atom_min_shared(sb + OFF_KEY + 4u * s3m1, key);
                 }
             }
-            if (tid == 0) sts32(sb + OFF_KEY + 4u * s3, 0xffffffffu);
+            if (!APPROX && tid == 0) sts32(sb + OFF_KEY + 4u * s3, 0xffffffffu);
 
             // ---- (C) compute antidiagonal r
             int st0 = 0, en0 = -1;
             bool valid = false;
+            // APPROX: the thread(s) owning columns t* and t*+1 post v[t*] and u[t*+1] of this antidiagonal as plain
+            // differences (extz2: minus the q+e offset of its stored form), for the scalar update one iteration later
+            auto approx_post = [&](int base) {
+                const int l0 = ap_t - base, l1 = l0 + 1;
+                if (l0 >= 0 && l0 < 16) { const uint32_t c = get_cell(V, l0); sts32(sb + OFF_APV + 4u * (uint32_t)par, (uint32_t)((DUAL ? (int)(int8_t)(c >> 8) : (int)((c >> 8) & 0xffu)) - K.bias)); }
+                if (l1 >= 0 && l1 < 16) { const uint32_t c = get_cell(U, l1); sts32(sb + OFF_APU + 4u * (uint32_t)par, (uint32_t)((DUAL ? (int)(int8_t)(c >> 8) : (int)((c >> 8) & 0xffu)) - K.bias)); }
+            };
             if (r < stop_r) {
                 band_limits(r, qlen, tlen, w, st0, en0);
                 if (st0 > en0) stop_r = r; else valid = true;
@@ -419,6 +451,8 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                     uint4 o;
                     dpx_cells<DUAL, TB, RIGHT>(U, V, X, Y, X2, Y2, S, XT0, VT0, X2T0, K, o);
                     if (TB) *reinterpret_cast<uint4*>(tb_page + (int64_t)tb_rip * T.pitch + (base - st)) = o;
+                    if (APPROX) approx_post(base);
+                    else {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {            // H[t] += v[t] - qe (:239-241)
                         uint32_t dv = prmt(V[k], 0u, extSel);
@@ -435,10 +469,13 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                         for (int k = 0; k < 8; ++k) Hr[k] = __vsub2(Hr[k], dd);
                     }
                     act_p = true;
+                    }
                 } else {
                     // ---- general path: band edges, first row, profile overhang, idle and re-arming vectors
-                    int32_t nbH = __shfl_up_sync(FULL, Hb + sext16(Hr[7] >> 16), 1);
-                    if (NW == 1) { int32_t h = __shfl_sync(FULL, Hb + sext16(Hr[7] >> 16), 31); if (lane == 0) nbH = h; }
+                    int32_t nbH = 0;
+                    if (!APPROX) nbH = __shfl_up_sync(FULL, Hb + sext16(Hr[7] >> 16), 1);
+                    if (APPROX) {}
+                    else if (NW == 1) { int32_t h = __shfl_sync(FULL, Hb + sext16(Hr[7] >> 16), 31); if (lane == 0) nbH = h; }
                     else if (lane == 0 && r > 0) nbH = (int32_t)lds32(sb + OFF_EDGE + (uint32_t)(ppar * NW + (warp + NW - 1) % NW) * 32u + 16u);
                     bool rearmed = false;
                     if (Vt < st_) {            // a vector that fell below the band re-arms NT vectors to the right
@@ -518,7 +555,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                         }
                         // H[en0-1] as the reference's H[] holds it (:231): the value of the previous antidiagonal
                         // while that lane was inside the band, else the value it had when it left the band
-                        {
+                        if (!APPROX) {
                             const int32_t hleft = ce > 0 ? Hb + sext16(get_cell(Hr, (ce - 1) & 15)) : nbH;
                             hprev_keep = (hi_edge && r > 0 && en0 > 0 && en0 - 1 >= st0p) ? hleft : hprev_keep;
                         }
@@ -526,7 +563,8 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                         uint4 o;
                         dpx_cells<DUAL, TB, RIGHT>(U, V, X, Y, X2, Y2, S, XT0, VT0, X2T0, K, o);
                         if (TB) *reinterpret_cast<uint4*>(tb_page + (int64_t)tb_rip * T.pitch + (base - st)) = o;
-
+                        if (APPROX) approx_post(base);
+                        else {
                         // exact max bookkeeping (:224-260): H[t] += v[t] - qe ; H[en0] from its left neighbour
                         const bool fix = hi_edge && (r == 0 || en0 > 0);
                         int32_t fixv;
@@ -564,6 +602,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                             for (int k = 0; k < 8; ++k) Hr[k] = __vsub2(Hr[k], dd);
                         }
                         act_p = true;
+                        }
                     }
                 }
                 habs_p = habs; st0p = st0; en0p = en0;
@@ -571,11 +610,13 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                 if (NW > 1 && lane == 31) {
                     const uint32_t ea = sb + OFF_EDGE + (uint32_t)(par * NW + warp) * 32u;
                     sts128(ea, make_uint4(X[7], V[7], DUAL ? X2[7] : 0u, qw));
-                    sts32(ea + 16u, (uint32_t)(Hb + sext16(Hr[7] >> 16)));
+                    if (!APPROX) sts32(ea + 16u, (uint32_t)(Hb + sext16(Hr[7] >> 16)));
                     if (wild) sts32(ea + 20u, amb);
                 }
-                const int32_t wmax = __reduce_max_sync(FULL, habs);
-                if (lane == 0) sts32(sb + OFF_MH + 4u * (uint32_t)(s3 * NW + warp), (uint32_t)wmax);
+                if (!APPROX) {
+                    const int32_t wmax = __reduce_max_sync(FULL, habs);
+                    if (lane == 0) sts32(sb + OFF_MH + 4u * (uint32_t)(s3 * NW + warp), (uint32_t)wmax);
+                }
                 if (TB && ++tb_rip == T.rows_per_page) {
                     tb_rip = 0; ++tb_pg;
                     if (tb_pg < T.tb_pages) tb_page = C.pool.base + (int64_t)table[tb_pg] * C.pool.page_bytes;
@@ -627,7 +668,8 @@ inline bool dpx_supports(const DevScoring& sc, const DevTask& t, bool has_wild)
 {
     (void)has_wild;            // wildcard bases: one extra bit per lane in the kernel (T.wild)
     if (t.kind != 1) return false;
-    if (t.flag & (FSV_EZ_GENERIC_SC | FSV_EZ_APPROX_MAX | FSV_EZ_APPROX_DROP)) return false;
+    if (t.flag & FSV_EZ_GENERIC_SC) return false;
+    if ((t.flag & FSV_EZ_APPROX_MAX) && !(t.flag & FSV_EZ_SCORE_ONLY)) return false;      // approximate maximum: score-only variant (TBM 3)
     if (sc.m != 5) return false;
     return dpx_class_of(dpx_warps_needed(t)) != 0;
 }
@@ -693,18 +735,18 @@ inline int dpx_launch_nw(cudaStream_t stream, int nw, int grid, bool excl, const
 #define FSV_DPX_FAMILY(D, T)                                                                                           \
     int dpx_grid_##D##T(int sm_count, int nw, int n_tasks);                                                           \
     int dpx_launch_##D##T(cudaStream_t stream, int nw, int grid, bool excl, const DpxParams& P, std::string* err);
-FSV_DPX_FAMILY(0, 0) FSV_DPX_FAMILY(0, 1) FSV_DPX_FAMILY(0, 2) FSV_DPX_FAMILY(1, 0) FSV_DPX_FAMILY(1, 1) FSV_DPX_FAMILY(1, 2)
+FSV_DPX_FAMILY(0, 0) FSV_DPX_FAMILY(0, 1) FSV_DPX_FAMILY(0, 2) FSV_DPX_FAMILY(0, 3) FSV_DPX_FAMILY(1, 0) FSV_DPX_FAMILY(1, 1) FSV_DPX_FAMILY(1, 2) FSV_DPX_FAMILY(1, 3)
 #undef FSV_DPX_FAMILY
 
 inline int dpx_grid(int sm_count, bool dual, int tbm, int nw, int n_tasks)
 {
-    if (dual) return tbm == 2 ? dpx_grid_12(sm_count, nw, n_tasks) : tbm ? dpx_grid_11(sm_count, nw, n_tasks) : dpx_grid_10(sm_count, nw, n_tasks);
-    return tbm == 2 ? dpx_grid_02(sm_count, nw, n_tasks) : tbm ? dpx_grid_01(sm_count, nw, n_tasks) : dpx_grid_00(sm_count, nw, n_tasks);
+    if (dual) return tbm == 3 ? dpx_grid_13(sm_count, nw, n_tasks) : tbm == 2 ? dpx_grid_12(sm_count, nw, n_tasks) : tbm ? dpx_grid_11(sm_count, nw, n_tasks) : dpx_grid_10(sm_count, nw, n_tasks);
+    return tbm == 3 ? dpx_grid_03(sm_count, nw, n_tasks) : tbm == 2 ? dpx_grid_02(sm_count, nw, n_tasks) : tbm ? dpx_grid_01(sm_count, nw, n_tasks) : dpx_grid_00(sm_count, nw, n_tasks);
 }
 inline int dpx_launch(cudaStream_t stream, bool dual, int tbm, int nw, int grid, bool excl, const DpxParams& P, std::string* err)
 {
-    if (dual) return tbm == 2 ? dpx_launch_12(stream, nw, grid, excl, P, err) : tbm ? dpx_launch_11(stream, nw, grid, excl, P, err) : dpx_launch_10(stream, nw, grid, excl, P, err);
-    return tbm == 2 ? dpx_launch_02(stream, nw, grid, excl, P, err) : tbm ? dpx_launch_01(stream, nw, grid, excl, P, err) : dpx_launch_00(stream, nw, grid, excl, P, err);
+    if (dual) return tbm == 3 ? dpx_launch_13(stream, nw, grid, excl, P, err) : tbm == 2 ? dpx_launch_12(stream, nw, grid, excl, P, err) : tbm ? dpx_launch_11(stream, nw, grid, excl, P, err) : dpx_launch_10(stream, nw, grid, excl, P, err);
+    return tbm == 3 ? dpx_launch_03(stream, nw, grid, excl, P, err) : tbm == 2 ? dpx_launch_02(stream, nw, grid, excl, P, err) : tbm ? dpx_launch_01(stream, nw, grid, excl, P, err) : dpx_launch_00(stream, nw, grid, excl, P, err);
 }
 
 }  // namespace fsv

@@ -303,6 +303,31 @@ def test_right_aligned_gaps_on_the_dpx_kernel(oracle, aligner, preset, w):
     assert any(not np.array_equal(task_cigar(res_l[i], cig_l), task_cigar(res_r[i], cig_r)) for i in range(len(res_l)))
 
 
+@pytest.mark.parametrize("preset,w", [("hifiasm", 500), ("asm5", 3001), ("map-ont", 60)])
+def test_approximate_maximum_score_only_on_the_dpx_kernel(oracle, aligner, preset, w):
+    """KSW_EZ_SCORE_ONLY | KSW_EZ_APPROX_MAX (| KSW_EZ_APPROX_DROP), hifiasm's call (Correct.cpp:7811,7956;
+    ksw2_extz2_sse.c:270-286): one cell is followed greedily, z-drop only with APPROX_DROP, mqe / mte never set."""
+    rng = np.random.default_rng(55 + w)
+    pairs, flags = [], []
+    base = _abi.EZ_SCORE_ONLY | _abi.EZ_APPROX_MAX
+    for i, L in enumerate([300, 1200, 2500, 4100, 5000, 6300, 800, 3300]):
+        ref = synth.random_seq(rng, L)
+        q = synth.mutate(rng, ref, 0.02, 0.01, 0.01)
+        if i % 4 == 1:                                   # diverges half way: APPROX_DROP must stop, plain approx must not
+            q = np.concatenate([q[:len(q) // 2], synth.random_seq(rng, len(q) // 2)])
+        if i % 4 == 2:
+            q = np.concatenate([q[:L // 3], synth.random_seq(rng, 90), q[L // 3:]])
+        pairs.append((q, ref))
+        flags.append(base | (_abi.EZ_APPROX_DROP if i % 2 else 0) | (_abi.EZ_EXTZ_ONLY if i % 3 == 0 else 0))
+    from focalsv_b200.presets import PRESETS
+    g = synth._pack("approx." + preset, preset, pairs, w, PRESETS[preset].zdrop, flags=np.array(flags, dtype=np.int32))
+    before = aligner.stats()["exact_path_tasks"]
+    bad, ores, gres = compare_group(oracle, aligner, g)
+    assert not bad, bad
+    assert aligner.stats()["exact_path_tasks"] == before
+    assert int(gres["zdropped"].sum()) >= 1 and all(int(x) == _abi.NEG_INF for x in gres["mqe"])
+
+
 def test_mixed_kernel_variants_share_the_pool(oracle, aligner):
     """One batch whose tasks land on several kernel variants at once (1/2/4-warp DPX classes, score-only and
     CIGAR, wildcard tasks, and right-aligned tasks on the general kernel), all running concurrently on one page pool."""
