@@ -308,11 +308,22 @@ def main():
     except Exception:
         pass
     tb_gbs = st1["traceback_bytes"] * args.steps / (fill_ms * 1e-3) / 1e9
+    # DRAM bytes of the fill launches of one step of THIS workload, from the committed ncu capture (profiles/);
+    # scaled by cells when the run uses another number of regions
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")) as fh:
+            tj = json.load(fh)
+        traffic = {"dram_bytes_per_step": tj["dram_bytes_per_step"] * (cells_step / tj["cells_per_step"]),
+                   "algorithmic_bytes_per_step": float(cells_step), "unit": "bytes (1 B traceback per in-band cell)",
+                   "source": "profiles/ncu_traffic_r1.json (ncu dram__bytes_read.sum + dram__bytes_write.sum of the fill launches)"}
+    except Exception:
+        pass
     roofline = {"bound": "int_alu", "kernel": "fsv_fill (DP fill incl. traceback store)",
                 "achieved": achieved, "peak": peak, "unit": "Tlane-op/s", "frac": achieved / peak,
                 "ops_per_cell": OPS_PER_CELL[kind], "cells_per_launch": cells_step / max(1, (st1["fill_launches"] - st0["fill_launches"]) // max(args.steps, 1)),
                 "peak_source": "measured in this run (fsv_measure_int_peak), best of " + ", ".join("%s=%.1f" % kv for kv in sorted(peaks.items())),
-                "traffic": None,
+                "traffic": traffic,
                 "hbm": {"achieved": tb_gbs, "peak": hbm_peak or 6650.0, "unit": "GB/s",
                         "frac": tb_gbs / (hbm_peak or 6650.0), "what": "traceback bytes written / fill time",
                         "peak_source": "MEASURED_PEAKS.json" if hbm_peak else "fallback"},
