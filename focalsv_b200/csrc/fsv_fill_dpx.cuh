@@ -226,7 +226,7 @@ __device__ __forceinline__ void dpx_cells(uint32_t (&U)[8], uint32_t (&V)[8], ui
     }
 }
 
-// EXCL only tags a second copy of the 6- and 8-warp kernels: it is launched with (almost) all of an SM's
+// EXCL only tags a second copy of each kernel: it is launched with (almost) all of an SM's
 // shared memory reserved, so that a CTA working on one of the few very long tasks has its SM to itself.
 // TBM: 0 = score only, 1 = traceback, ties to the left (default), 2 = traceback, ties to the right (KSW_EZ_RIGHT),
 // 3 = score only with KSW_EZ_APPROX_MAX (:270-286): no H[] at all, one cell is followed greedily.
@@ -692,8 +692,8 @@ inline int dpx_launch_one(cudaStream_t stream, int grid, bool excl, const DpxPar
     cudaError_t e = cudaSuccess;
     DpxParams PK = P;
     PK.K = DpxConst<DUAL, TBM == 2>(P.C.sc);
-    if (excl && NW >= 6) {
-        auto kern = fsv_fill_dpx_kernel<DUAL, TBM, (NW >= 6 ? NW : 6), true>;
+    if (excl) {
+        auto kern = fsv_fill_dpx_kernel<DUAL, TBM, NW, true>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DPX_EXCL_SMEM);
         if (e == cudaSuccess) kern<<<grid, NW * 32, DPX_EXCL_SMEM, stream>>>(PK);
     } else {
