@@ -42,7 +42,8 @@ RESULT_DTYPE = np.dtype([("max", "<i4"), ("zdropped", "<i4"), ("max_q", "<i4"), 
                          ("cigar_off", "<i8"), ("cells", "<i8")], align=True)
 SIGNATURE_DTYPE = np.dtype([("task", "<i4"), ("svtype", "<i4"), ("pos", "<i8"), ("svlen", "<i4"), ("read_start", "<i4"),
                             ("read_end", "<i4"), ("pad_", "<i4")], align=True)
-assert TASK_DTYPE.itemsize == 40 and RESULT_DTYPE.itemsize == 64 and SIGNATURE_DTYPE.itemsize == 32
+PAIR_DTYPE = np.dtype([("a_off", "<i8"), ("b_off", "<i8"), ("a_len", "<i4"), ("b_len", "<i4")], align=True)
+assert TASK_DTYPE.itemsize == 40 and RESULT_DTYPE.itemsize == 64 and SIGNATURE_DTYPE.itemsize == 32 and PAIR_DTYPE.itemsize == 24
 
 # fields that must be bit-identical to ksw_extz_t (ksw2.h:23-32)
 EZ_FIELDS = ("max", "zdropped", "max_q", "max_t", "mqe", "mqe_t", "mte", "mte_q", "score", "reach_end", "n_cigar")

@@ -20,7 +20,7 @@ LIB_PATH = os.environ.get("FSV_LIB_PATH") or os.path.join(_HERE, "libfocalsv_cud
 EXPORTS = ("fsv_init", "fsv_destroy", "fsv_strerror", "fsv_last_error", "fsv_abi_version", "fsv_device_count",
            "fsv_get_stats", "fsv_set_option", "fsv_align_batch", "fsv_batch_create", "fsv_batch_run",
            "fsv_batch_fetch", "fsv_batch_destroy", "fsv_ksw_extz2", "fsv_ksw_extd2", "fsv_task_cells",
-           "fsv_lpt_bins", "fsv_measure_int_peak", "fsv_batch_timeline", "fsv_batch_signatures")
+           "fsv_lpt_bins", "fsv_measure_int_peak", "fsv_batch_timeline", "fsv_batch_signatures", "fsv_edit_distance_batch")
 
 _lib = None
 
@@ -58,6 +58,7 @@ def load_library(path=None):
     lib.fsv_batch_destroy.argtypes = [vp]
     lib.fsv_batch_timeline.argtypes = [vp, vp]
     lib.fsv_batch_signatures.argtypes = [vp, vp, C.c_int, vp, sz, C.POINTER(sz)]
+    lib.fsv_edit_distance_batch.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp]
     lib.fsv_batch_destroy.restype = None
     lib.fsv_task_cells.argtypes = [i32, i32, i32]
     lib.fsv_task_cells.restype = i64
@@ -168,6 +169,28 @@ class Aligner(object):
             raise FsvError(rc, "cigar arena too small: need %d words" % used.value)
         self._check(rc, "fsv_align_batch")
         return out, cig[:used.value]
+
+    def edit_distances(self, seqs_a, seqs_b):
+        """Global unit-cost edit distance of seqs_a[i] vs seqs_b[i] (what the reference asks edlib for,
+        remove_redundancy.py:57-63).  Sequences: str, bytes or uint8 arrays.  Returns an int32 array."""
+        def arena(seqs):
+            bufs = [np.frombuffer(s.encode() if isinstance(s, str) else bytes(s), dtype=np.uint8) if not isinstance(s, np.ndarray)
+                    else np.ascontiguousarray(s, dtype=np.uint8) for s in seqs]
+            lens = np.array([len(x) for x in bufs], dtype=np.int64)
+            offs = np.concatenate([[0], np.cumsum(lens)[:-1]]) if len(bufs) else np.zeros(0, np.int64)
+            return (np.concatenate(bufs) if len(bufs) and lens.sum() else np.zeros(1, np.uint8)), offs, lens
+        if len(seqs_a) != len(seqs_b):
+            raise ValueError("edit_distances needs as many a as b sequences")
+        a, ao, al_ = arena(seqs_a)
+        b, bo, bl = arena(seqs_b)
+        n = len(al_)
+        pairs = np.zeros(n, dtype=_abi.PAIR_DTYPE)
+        pairs["a_off"], pairs["b_off"], pairs["a_len"], pairs["b_len"] = ao, bo, al_, bl
+        out = np.zeros(max(n, 1), dtype=np.int32)
+        rc = self._lib.fsv_edit_distance_batch(self._h, a.ctypes.data, int(al_.sum()), b.ctypes.data, int(bl.sum()),
+                                               pairs.ctypes.data, n, out.ctypes.data)
+        self._check(rc, "fsv_edit_distance_batch")
+        return out[:n]
 
     def batch(self, sc, qarena, tarena, tasks):
         return Batch(self, sc, qarena, tarena, tasks)

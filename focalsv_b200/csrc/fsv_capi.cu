@@ -22,6 +22,7 @@
 #include "fsv_fill_dpx.cuh"
 #include "fsv_fill_exact.cuh"
 #include "fsv_peaks.cuh"
+#include "fsv_editdist.cuh"
 #include "fsv_signatures.cuh"
 
 using namespace fsv;
@@ -703,6 +704,79 @@ extern "C" int fsv_batch_fetch(fsv_batch* b, fsv_result* out, uint32_t* cigar, s
         c->stats.d2h_bytes += used * 4;
     }
     return FSV_OK;
+}
+
+extern "C" int fsv_edit_distance_batch(fsv_ctx* c, const uint8_t* a_arena, size_t a_bytes, const uint8_t* b_arena, size_t b_bytes,
+                                       const fsv_pair* pairs, size_t n, int32_t* dist)
+{
+    if (!c || (n && (!pairs || !dist)) || n > 0x7ffffff0u) return FSV_ERR_INVALID;
+    if (!n) return FSV_OK;
+    CK(c, cudaSetDevice(c->device));
+    // ---- bounds, the symbol remap (at most 8 distinct byte values) and the work order
+    int remap[256]; bool seen[256] = {false};
+    int64_t max_b = 1;
+    for (size_t i = 0; i < n; ++i) {
+        const fsv_pair& p = pairs[i];
+        if (p.a_len < 0 || p.b_len < 0 || p.a_off < 0 || p.b_off < 0 || (uint64_t)p.a_off + (uint64_t)p.a_len > a_bytes ||
+            (uint64_t)p.b_off + (uint64_t)p.b_len > b_bytes) { c->last_error = "pair " + std::to_string(i) + " points outside the arenas"; return FSV_ERR_INVALID; }
+        if (p.a_len && p.b_len) {
+            for (int k = 0; k < p.a_len; ++k) seen[a_arena[p.a_off + k]] = true;
+            for (int k = 0; k < p.b_len; ++k) seen[b_arena[p.b_off + k]] = true;
+            max_b = std::max<int64_t>(max_b, p.b_len);
+        }
+    }
+    int n_sym = 0;
+    for (int v = 0; v < 256; ++v) { remap[v] = 0; if (seen[v]) remap[v] = n_sym++; }
+    if (n_sym > ED_MAX_SYMBOLS) { c->last_error = "more than 8 distinct byte values in one edit-distance call"; return FSV_ERR_INVALID; }
+    std::vector<uint8_t> ra(a_bytes + 1), rb(b_bytes + 1);
+    for (size_t i = 0; i < a_bytes; ++i) ra[i] = (uint8_t)remap[a_arena[i]];
+    for (size_t i = 0; i < b_bytes; ++i) rb[i] = (uint8_t)remap[b_arena[i]];
+    std::vector<int32_t> order(n);
+    for (size_t i = 0; i < n; ++i) order[i] = (int32_t)i;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
+        return (int64_t)pairs[x].a_len * pairs[x].b_len > (int64_t)pairs[y].a_len * pairs[y].b_len; });
+    // ---- device buffers (cached blocks of the context)
+    const int warps_per_cta = 4;
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((n + warps_per_cta - 1) / warps_per_cta, (size_t)c->sm_count * 4));
+    const int64_t pitch = (max_b + 15) / 16 * 16;
+    size_t sz[7] = {0};
+    uint8_t* d_a = (uint8_t*)dev_alloc(c, a_bytes + 16, &sz[0]);
+    uint8_t* d_b = (uint8_t*)dev_alloc(c, b_bytes + 16, &sz[1]);
+    fsv_pair* d_pairs = (fsv_pair*)dev_alloc(c, n * sizeof(fsv_pair), &sz[2]);
+    int32_t* d_order = (int32_t*)dev_alloc(c, n * 4, &sz[3]);
+    int32_t* d_dist = (int32_t*)dev_alloc(c, n * 4, &sz[4]);
+    int8_t* d_carry = (int8_t*)dev_alloc(c, (size_t)grid * warps_per_cta * (size_t)pitch, &sz[5]);
+    unsigned int* d_cursor = (unsigned int*)dev_alloc(c, 64, &sz[6]);
+    auto done = [&](int code) {
+        dev_release(c, d_a, sz[0]); dev_release(c, d_b, sz[1]); dev_release(c, d_pairs, sz[2]); dev_release(c, d_order, sz[3]);
+        dev_release(c, d_dist, sz[4]); dev_release(c, d_carry, sz[5]); dev_release(c, d_cursor, sz[6]);
+        return code;
+    };
+    if (!d_a || !d_b || !d_pairs || !d_order || !d_dist || !d_carry || !d_cursor) return done(FSV_ERR_NOMEM);
+#define CKE(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { c->last_error = std::string(#call) + " -> " + cudaGetErrorString(e_); cudaGetLastError(); return done(FSV_ERR_CUDA); } } while (0)
+    CKE(cudaMemcpyAsync(d_a, ra.data(), a_bytes, cudaMemcpyHostToDevice, c->stream));
+    CKE(cudaMemcpyAsync(d_b, rb.data(), b_bytes, cudaMemcpyHostToDevice, c->stream));
+    CKE(cudaMemcpyAsync(d_pairs, pairs, n * sizeof(fsv_pair), cudaMemcpyHostToDevice, c->stream));
+    CKE(cudaMemcpyAsync(d_order, order.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
+    CKE(cudaMemsetAsync(d_cursor, 0, 64, c->stream));
+    EdParams P{d_a, d_b, d_pairs, d_order, (int32_t)n, d_dist, d_carry, pitch, d_cursor};
+    cudaEvent_t e0, e1;
+    CKE(cudaEventCreate(&e0)); CKE(cudaEventCreate(&e1));
+    CKE(cudaEventRecord(e0, c->stream));
+    fsv_edit_distance_kernel<<<grid, warps_per_cta * 32, 0, c->stream>>>(P);
+    CKE(cudaGetLastError());
+    CKE(cudaEventRecord(e1, c->stream));
+    CKE(cudaMemcpyAsync(dist, d_dist, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CKE(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+#undef CKE
+    c->stats.other_launches += 1;
+    c->stats.total_ms = ms;
+    c->stats.h2d_bytes += (int64_t)(a_bytes + b_bytes + n * (sizeof(fsv_pair) + 4));
+    c->stats.d2h_bytes += (int64_t)n * 4;
+    return done(FSV_OK);
 }
 
 extern "C" int fsv_batch_signatures(fsv_batch* b, const int64_t* ref_start, int min_svlen, fsv_signature* out, size_t cap, size_t* n_out)

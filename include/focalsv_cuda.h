@@ -180,6 +180,19 @@ typedef struct fsv_signature {
 int fsv_batch_signatures(fsv_batch* batch, const int64_t* ref_start, int min_svlen,
                          fsv_signature* out, size_t cap, size_t* n_out);
 
+/* ---- next row: batched global edit distance -----------------------------
+ * What the reference computes with edlib.align(seq1, seq2)["editDistance"] (default mode NW, k = -1: the plain
+ * unit-cost Levenshtein distance) when it de-duplicates INS alleles
+ * (focalsv/4_sv_calling/Dippav/remove_redundancy.py:57-63, remove_redundancy_region_based.py:123-128).
+ * Sequences are raw bytes compared for equality (ASCII or codes); at most 8 distinct byte values may occur in one
+ * call (DNA + N), otherwise FSV_ERR_INVALID.  dist[i] = distance of pair i; an empty sequence gives the other's length. */
+typedef struct fsv_pair {
+    int64_t a_off, b_off;     /* byte offsets into the two arenas */
+    int32_t a_len, b_len;
+} fsv_pair;
+int fsv_edit_distance_batch(fsv_ctx* ctx, const uint8_t* a_arena, size_t a_bytes, const uint8_t* b_arena, size_t b_bytes,
+                            const fsv_pair* pairs, size_t n_pairs, int32_t* dist);
+
 /* ---- single-task convenience, argument-for-argument ksw2.h:54-61 ------
  * (km dropped; ez -> fsv_result + caller-owned cigar buffer). */
 int fsv_ksw_extz2(fsv_ctx* ctx, int qlen, const uint8_t* query, int tlen, const uint8_t* target,

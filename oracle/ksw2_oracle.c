@@ -386,6 +386,31 @@ int fsvo_extz2(int qlen, const uint8_t* query, int tlen, const uint8_t* target, 
 
 
 /* ---------------------------------------------------------------------- */
+/* Global unit-cost edit distance, the value edlib.align(a, b)["editDistance"] returns in its default mode (NW,
+ * k = -1) at focalsv/4_sv_calling/Dippav/remove_redundancy.py:57-63: textbook two-row Levenshtein DP. */
+int32_t fsvo_edit_distance(int alen, const uint8_t* a, int blen, const uint8_t* b)
+{
+    int32_t *prev, *cur, *tmp, r;
+    int i, j;
+    if (alen <= 0) return blen > 0 ? blen : 0;
+    if (blen <= 0) return alen;
+    prev = (int32_t*)malloc(((size_t)blen + 1) * sizeof(int32_t)); cur = (int32_t*)malloc(((size_t)blen + 1) * sizeof(int32_t));
+    if (!prev || !cur) { free(prev); free(cur); return -1; }
+    for (j = 0; j <= blen; ++j) prev[j] = j;
+    for (i = 1; i <= alen; ++i) {
+        cur[0] = i;
+        for (j = 1; j <= blen; ++j) {
+            int32_t d = prev[j - 1] + (a[i - 1] != b[j - 1]), u = prev[j] + 1, l = cur[j - 1] + 1;
+            d = d < u ? d : u; cur[j] = d < l ? d : l;
+        }
+        tmp = prev; prev = cur; cur = tmp;
+    }
+    r = prev[blen];
+    free(prev); free(cur);
+    return r;
+}
+
+/* ---------------------------------------------------------------------- */
 /* The same dual-affine lane arithmetic as the loop in fsvo_extd2, written so that gcc vectorises it
  * (16 int8 lanes per SSE register, like the reference's own SSE build): the t-1 operands are first
  * copied into shifted scratch rows, then every lane is independent.  Used when no diagnostics are

@@ -34,6 +34,8 @@ int32_t fsvo_score_cigar(int qlen, const uint8_t* query, int tlen, const uint8_t
 int fsvo_run_batch(const fsv_scoring* sc, const uint8_t* qarena, const uint8_t* tarena,
                    const fsv_task* tasks, int64_t n, int threads, fsv_result* out,
                    uint32_t* cigar_arena, int64_t cigar_cap, int64_t* cigar_used);
+/* global unit-cost edit distance (what edlib.align(a, b)["editDistance"] returns, remove_redundancy.py:57-63) */
+int32_t fsvo_edit_distance(int alen, const uint8_t* a, int blen, const uint8_t* b);
 #ifdef __cplusplus
 }
 #endif

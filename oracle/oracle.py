@@ -43,6 +43,7 @@ ref = C.CDLL(_REF) if _REF else None
 
 port.fsvo_task_cells.restype = C.c_int64
 port.fsvo_gotoh2_global.restype = C.c_int32
+port.fsvo_edit_distance.restype = C.c_int32
 port.fsvo_score_cigar.restype = C.c_int32
 
 
@@ -114,6 +115,13 @@ def gotoh2_global(query, target, sc):
     return int(port.fsvo_gotoh2_global(C.c_int(len(query)), _ptr(query, _u8p), C.c_int(len(target)),
                                        _ptr(target, _u8p), C.c_int(sc.m), _ptr(mat, _i8p),
                                        C.c_int(sc.q), C.c_int(sc.e), C.c_int(q2), C.c_int(e2)))
+
+
+def edit_distance(a, b):
+    """Global unit-cost edit distance of two byte sequences (edlib.align(a, b)["editDistance"], mode NW)."""
+    a = np.frombuffer(a.encode() if isinstance(a, str) else bytes(a), dtype=np.uint8) if not isinstance(a, np.ndarray) else _as_u8(a)
+    b = np.frombuffer(b.encode() if isinstance(b, str) else bytes(b), dtype=np.uint8) if not isinstance(b, np.ndarray) else _as_u8(b)
+    return int(port.fsvo_edit_distance(C.c_int(len(a)), _ptr(a, _u8p), C.c_int(len(b)), _ptr(b, _u8p)))
 
 
 def score_cigar(query, target, sc, cigar):
