@@ -43,6 +43,10 @@ def parse_args():
     ap.add_argument("--regions", type=int, default=int(os.environ.get("FSV_BENCH_REGIONS", 5000)),
                     help="regions per GPU (configs[1] = 5000)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per reference step / baseline sample")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"],
+                    help="cfg2 = BASELINE configs[1] (the metric's config, default); cfg3 = BASELINE configs[2]'s single-affine "
+                         "contig tasks (a=2,b=4,q=4,e=2,w=500,z=400): the one workload whose CPU arm is the reference's OWN "
+                         "ksw2_extz2_sse.c compiled in place (cpu_baseline.kind = reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--force-exact", action="store_true", help="use only the general int8-exact kernel")
@@ -53,9 +57,15 @@ def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
+WORKLOAD = "cfg2"      # set from --workload in main()
+
+
 def build_shard(rank, world, regions_per_gpu):
     """Region lengths of the whole job (world x regions_per_gpu), LPT-binned by estimated cells;
     this rank synthesises only its own bin."""
+    if WORKLOAD == "cfg3":      # every rank its own 1/world-independent share (weak scaling), single-affine contig tasks
+        g = synth.config3(n_regions=regions_per_gpu, seed=1003 + 7919 * rank, max_region=400000)[0]
+        return g, regions_per_gpu
     rng = np.random.default_rng(CONFIG_SEED)
     lens = synth.sample_quantiles(rng, synth.REGION_LEN_Q, regions_per_gpu * world)
     if world > 1:
@@ -164,7 +174,7 @@ def reference_arm(args, rank, world):
         c, dt, kind = run_cpu(group, idx, cores)
         cells += c; secs += dt
     gcups = cells / secs / 1e9
-    sample = "%d of %d tasks of cfg2 (seed %d), %.3g cells/step" % (len(idx), len(group.tasks), CONFIG_SEED, cells / max(args.steps, 1))
+    sample = "%d of %d tasks of %s (seed %d), %.3g cells/step" % (len(idx), len(group.tasks), WORKLOAD, CONFIG_SEED, cells / max(args.steps, 1))
     line = {"impl": "reference", "metric": "alignment_gcups", "value": gcups, "unit": "GCUPS", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / max(args.steps, 1) * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
@@ -172,12 +182,20 @@ def reference_arm(args, rank, world):
             "config": workload_config(args, world, n_regions),
             "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "dual-affine ksw_extd2_sse is not in /root/reference (minimap2 2.24 dependency); the CPU arm is the "
-                    "oracle's plain-C restatement (gcc -O3 -msse4.1), one task per thread, all host threads"}
+            "note": ("the reference's own software/hifiasm-0.16.1/ksw2_extz2_sse.c, compiled in place into oracle/_ref "
+                     "(gcc -O3 -msse4.1), one task per thread, all host threads") if kind == "reference" else
+                    ("dual-affine ksw_extd2_sse is not in /root/reference (minimap2 2.24 dependency); the CPU arm is the "
+                     "oracle's plain-C restatement (gcc -O3 -msse4.1 + AVX2 clone), one task per thread, all host threads")}
     print(json.dumps(line), flush=True)
 
 
 def workload_config(args, world, n_regions):
+    if WORKLOAD == "cfg3":
+        return {"workload": "BASELINE configs[2] (contig tasks): %d regions x 2 contigs per GPU, 1 %% error, single-affine a=2,b=4,q=4,e=2 "
+                            "(hifiasm's in-tree constants, Correct.h:1194-1199), band 500, zdrop 400, global / EXTZ_ONLY + CIGAR; regions capped at 400 kb" % args.regions,
+                "regions_per_gpu": args.regions, "regions_this_rank": n_regions, "tasks_per_region": 2, "seed": 1003,
+                "sharding": "independent shares per rank, no collective", "world": world,
+                "l2_policy": "inputs+traceback per step exceed the 126 MB L2"}
     return {"workload": "BASELINE configs[1]: FocalSV auto mode, %d SV-rich regions x 2 haplotype contigs per GPU vs "
                         "hg38-shaped windows, asm5 (a=1,b=19,q=39,e=3,q2=81,e2=1), band 3001, zdrop 200, global + CIGAR"
                         % args.regions,
@@ -188,6 +206,10 @@ def workload_config(args, world, n_regions):
 
 def main():
     args = parse_args()
+    global WORKLOAD
+    WORKLOAD = args.workload
+    if WORKLOAD == "cfg3" and args.regions == 5000:
+        args.regions = 2000                  # BASELINE configs[2]: 2 000 regions
     rank, local_rank, world = dist_env()
     if args.impl == "reference":
         reference_arm(args, rank, world)
@@ -312,6 +334,8 @@ def main():
     # scaled by cells when the run uses another number of regions
     traffic = None
     try:
+        if WORKLOAD != "cfg2":
+            raise KeyError("the committed capture is of cfg2")
         with open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")) as fh:
             tj = json.load(fh)
         traffic = {"dram_bytes_per_step": tj["dram_bytes_per_step"] * (cells_step / tj["cells_per_step"]),
