@@ -45,7 +45,7 @@ struct fsv_ctx {
     int sm_count = 0;
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;            // copies, timing events
-    cudaStream_t kstream[48] = {};            // one per concurrently running fill-kernel variant
+    cudaStream_t kstream[56] = {};            // one per concurrently running fill-kernel variant
     std::string last_error;
     fsv_stats stats{};
     // options
@@ -54,6 +54,8 @@ struct fsv_ctx {
     int force_excl = 0;         // experiment: every DPX task on the exclusive (one CTA per SM) launch
     int exact_smem_lanes = 4096;
     int64_t page_bytes = 32ll << 20;
+    int64_t segment_min_diags = 0;   // tasks with at least this many antidiagonals are cut into segments (0 = off)
+    int64_t segment_rows = 65536;    // target antidiagonals per segment (rounded up to whole traceback pages)
     int lazy_min_pages = 16;    // DPX tasks with at least this many traceback pages take them as they advance (0 = all up front)
     int pool_stall_ms = 60000;  // lazy-pool watchdog
     int lazy_fill_pct = 65;     // admission of such a task waits while the projected peak of those running exceeds this share of the pool
@@ -124,6 +126,7 @@ struct fsv_batch {
     int64_t ws_lanes = 0;
     int64_t pool_pages = 0;           // pages of the traceback pool this batch wants
     int64_t pages_total = 0;          // pages all its tasks need together
+    int64_t cap_pages = 0;            // pages the pool may have at most (memory budget)
     int32_t max_pages_per_task = 1;
     int64_t tb_bytes_total = 0;       // traceback bytes a full run writes
     int64_t max_rows = 1;             // antidiagonals of the longest task that stores traceback
@@ -138,6 +141,17 @@ struct fsv_batch {
     long long* d_timeline = nullptr;
     size_t sz_q = 0, sz_t = 0, sz_tasks = 0, sz_work = 0, sz_results = 0, sz_ctrl = 0, sz_cursor = 0, sz_cigar = 0, sz_timeline = 0;
     int state = 0;                    // 0 created, 1 run
+    // segmented tasks
+    std::vector<DevSeg> segs;
+    std::vector<SegTask> seg_tasks;
+    std::vector<int32_t> seg_pages;       // page-table entries (static pages from the top of the pool), per segmented task
+    int64_t seg_static_pages = 0, seg_rec_total = 0, seg_snap_words = 0;
+    struct SegLaunch { int nw, begin, count; };
+    std::vector<SegLaunch> seg_launches;  // slices of seg_work
+    std::vector<int32_t> seg_work;        // segment indices per launch
+    DevSeg* d_segs = nullptr; SegTask* d_seg_tasks = nullptr; int32_t* d_seg_tables = nullptr; int32_t* d_seg_work = nullptr;
+    int32_t* d_seg_done = nullptr; int32_t* d_seg_foot = nullptr; int4* d_seg_rec = nullptr; uint32_t* d_seg_snap = nullptr;
+    size_t sz_seg[8] = {0};
 };
 
 static const char* kErr[] = {"ok", "no CUDA device (libfocalsv_cuda has no CPU path)", "CUDA runtime error",
@@ -228,6 +242,8 @@ extern "C" int fsv_set_option(fsv_ctx* c, const char* key, int64_t value)
         if (value < 0 || value > (1 << 20)) return FSV_ERR_INVALID;
         c->lazy_min_pages = value == 0 ? 0 : (int)std::max<int64_t>(value, 3); return FSV_OK;
     }
+    if (!strcmp(key, "segment_min_diags")) { if (value < 0) return FSV_ERR_INVALID; c->segment_min_diags = value; return FSV_OK; }
+    if (!strcmp(key, "segment_rows")) { if (value < 1024) return FSV_ERR_INVALID; c->segment_rows = value; return FSV_OK; }
     if (!strcmp(key, "pool_stall_ms")) { if (value < 100) return FSV_ERR_INVALID; c->pool_stall_ms = (int)value; return FSV_OK; }
     if (!strcmp(key, "lazy_fill_pct")) {
         if (value < 1 || value > 100) return FSV_ERR_INVALID;
@@ -328,6 +344,11 @@ static void free_batch_device(fsv_batch* b)
     dev_release(c, b->d_cursor, b->sz_cursor); dev_release(c, b->d_cigar, b->sz_cigar); dev_release(c, b->d_timeline, b->sz_timeline);
     b->d_q = b->d_t = nullptr; b->d_tasks = nullptr; b->d_work = nullptr; b->d_results = nullptr; b->d_ctrl = nullptr;
     b->d_cursor = nullptr; b->d_cigar = nullptr; b->d_timeline = nullptr;
+    dev_release(c, b->d_segs, b->sz_seg[0]); dev_release(c, b->d_seg_tasks, b->sz_seg[1]); dev_release(c, b->d_seg_tables, b->sz_seg[2]);
+    dev_release(c, b->d_seg_work, b->sz_seg[3]); dev_release(c, b->d_seg_done, b->sz_seg[4]); dev_release(c, b->d_seg_foot, b->sz_seg[5]);
+    dev_release(c, b->d_seg_rec, b->sz_seg[6]); dev_release(c, b->d_seg_snap, b->sz_seg[7]);
+    b->d_segs = nullptr; b->d_seg_tasks = nullptr; b->d_seg_tables = nullptr; b->d_seg_work = nullptr; b->d_seg_done = nullptr;
+    b->d_seg_foot = nullptr; b->d_seg_rec = nullptr; b->d_seg_snap = nullptr;
 }
 
 extern "C" void fsv_batch_destroy(fsv_batch* b)
@@ -403,7 +424,7 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
         memset(&d, 0, sizeof d);
         d.q_off = t.q_off; d.t_off = t.t_off; d.qlen = t.qlen; d.tlen = t.tlen;
         d.zdrop = t.zdrop; d.end_bonus = t.end_bonus; d.flag = t.flag; d.orig = (int32_t)i; d.tb_off = -1;
-        d.kind = 1; d.rows_per_page = 1;
+        d.kind = 1; d.rows_per_page = 1; d.seg_id = -1;
         if (all_reset || t.qlen <= 0 || t.tlen <= 0) { d.kind = 0; d.pad_ = all_reset ? reset_status : 0; continue; }
         if (t.q_off < 0 || t.t_off < 0 || (uint64_t)t.q_off + (uint64_t)t.qlen > qbytes ||
             (uint64_t)t.t_off + (uint64_t)t.tlen > tbytes || (int64_t)t.qlen + t.tlen > 0x7ffffff0) {
@@ -455,6 +476,7 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
         int64_t cap_pages = std::max<int64_t>(budget / c->page_bytes, 0);
         b->pool_pages = std::min(pages_total, cap_pages);
         b->pages_total = pages_total;
+        b->cap_pages = cap_pages;
         if (b->max_pages_per_task > 1 || pages_total > 0)
             if (b->pool_pages < b->max_pages_per_task) {
                 c->last_error = "the traceback of the largest task (" + std::to_string(b->max_pages_per_task) +
@@ -468,6 +490,51 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
     std::vector<int32_t> ord(n);
     for (size_t i = 0; i < n; ++i) ord[i] = (int32_t)i;
     std::stable_sort(ord.begin(), ord.end(), [&](int32_t a, int32_t x) { return b->tasks[a].cells_est > b->tasks[x].cells_est; });
+    // ---- segmented tasks (fsv_common.cuh, DevSeg): the longest left-aligned CIGAR tasks are cut into segments of whole
+    // traceback pages; their pages are static (taken from the top of the pool), at most 45 % of it
+    std::vector<uint8_t> is_seg(n, 0);
+    if (c->segment_min_diags > 0) {
+        std::vector<int32_t> by_len;
+        for (size_t i = 0; i < n; ++i) {
+            const DevTask& d = b->tasks[i];
+            if (b->is_dpx[i] && d.tb_pages > 0 && !(d.flag & (FSV_EZ_RIGHT | FSV_EZ_SCORE_ONLY | FSV_EZ_APPROX_MAX)) && d.w >= 64 &&
+                (int64_t)d.qlen + d.tlen - 1 >= c->segment_min_diags) by_len.push_back((int32_t)i);
+        }
+        std::stable_sort(by_len.begin(), by_len.end(), [&](int32_t a, int32_t x) { return b->tasks[a].qlen + b->tasks[a].tlen > b->tasks[x].qlen + b->tasks[x].tlen; });
+        std::vector<std::vector<int32_t>> per_nw(9);
+        for (int32_t ti : by_len) {
+            DevTask& d = b->tasks[(size_t)ti];
+            const int64_t n_diag = (int64_t)d.qlen + d.tlen - 1;
+            const int64_t rpp = d.rows_per_page;
+            const int64_t seg_rows = std::max<int64_t>(1, (c->segment_rows + rpp - 1) / rpp) * rpp;      // whole pages
+            const int64_t warm = 5ll * d.w + 1024;                    // measured: the whole band is bit-identical about 4w antidiagonals after a cold start
+            const int n_segs = (int)((n_diag + seg_rows - 1) / seg_rows);
+            if (n_segs < 2 || seg_rows < 2 * warm) continue;
+            if ((b->seg_static_pages + d.tb_pages) * 100 > b->cap_pages * 45) continue;
+            SegTask st{};
+            st.rec_off = b->seg_rec_total; st.snap_off = b->seg_snap_words; st.table_off = (int32_t)b->seg_pages.size();
+            st.n_segs = n_segs; st.first_seg = (int32_t)b->segs.size();
+            b->seg_rec_total += n_diag;
+            b->seg_snap_words += (int64_t)2 * (n_segs - 1) * SEG_SNAP_WORDS;
+            for (int pg = 0; pg < d.tb_pages; ++pg) b->seg_pages.push_back((int32_t)(b->pool_pages - 1 - (b->seg_static_pages + pg)));
+            b->seg_static_pages += d.tb_pages;
+            d.seg_id = (int32_t)b->seg_tasks.size();
+            for (int k = 0; k < n_segs; ++k) {
+                DevSeg g{};
+                g.task = ti; g.index = k; g.count = n_segs;
+                g.r_begin = (int32_t)(k * seg_rows); g.r_end = (int32_t)std::min<int64_t>((k + 1) * seg_rows, n_diag);
+                g.r0 = (int32_t)std::max<int64_t>(0, g.r_begin - warm);
+                per_nw[(size_t)d.nw].push_back((int32_t)b->segs.size());
+                b->segs.push_back(g);
+            }
+            b->seg_tasks.push_back(st);
+            is_seg[(size_t)ti] = 1;
+        }
+        for (int nw = 8; nw >= 1; --nw) if (!per_nw[(size_t)nw].empty()) {
+            b->seg_launches.push_back({nw, (int)b->seg_work.size(), (int)per_nw[(size_t)nw].size()});
+            b->seg_work.insert(b->seg_work.end(), per_nw[(size_t)nw].begin(), per_nw[(size_t)nw].end());
+        }
+    }
     // Tasks long enough to decide the batch time by themselves get an SM each ("exclusive" launch): nothing can
     // shorten a task's chain of antidiagonals, but a CTA that has its SM to itself steps through it faster
     // (measured: 1.2-1.3 us per antidiagonal alone, 1.55-2.0 us when the SM is full).  Planning model, in
@@ -480,7 +547,7 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
         auto t_solo = [](int nw) { return nw >= 6 ? 1.3e-6 : 1.2e-6; };
         auto occ = [](int nw) { return nw == 1 ? 12.0 : nw == 2 ? 6.0 : nw == 4 ? 3.0 : 2.0; };
         std::vector<int> dpx;                       // DPX tasks, longest chain of antidiagonals first
-        for (size_t k = 0; k < n; ++k) if (b->is_dpx[ord[k]]) dpx.push_back(ord[k]);
+        for (size_t k = 0; k < n; ++k) if (b->is_dpx[ord[k]] && !is_seg[(size_t)ord[k]]) dpx.push_back(ord[k]);
         std::stable_sort(dpx.begin(), dpx.end(), [&](int a, int x) { return b->tasks[a].qlen + b->tasks[a].tlen > b->tasks[x].qlen + b->tasks[x].tlen; });
         const int S = c->sm_count, m = (int)dpx.size();
         auto nd = [&](int i) { return (double)(b->tasks[dpx[(size_t)i]].qlen + b->tasks[dpx[(size_t)i]].tlen); };
@@ -508,6 +575,7 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
         for (size_t k = 0; k < n; ++k) {
             const int ti = ord[k];
             const DevTask& d = b->tasks[ti];
+            if (is_seg[(size_t)ti]) continue;
             if (kind == 0) { if (b->is_dpx[ti]) continue; }
             else if (!b->is_dpx[ti] || d.nw != nw || ((d.flag & FSV_EZ_SCORE_ONLY) ? ((d.flag & FSV_EZ_APPROX_MAX) ? 3 : 0) : (d.flag & FSV_EZ_RIGHT) ? 2 : 1) != with_tb || (int)is_excl[ti] != excl) continue;
             b->work.push_back(ti);
@@ -554,6 +622,16 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
     DEV(d_cursor, sz_cursor, 64);
     DEV(d_cigar, sz_cigar, (size_t)(b->cigar_cap_words + 4) * 4);
     DEV(d_timeline, sz_timeline, (n + 1) * 16);
+    if (!b->segs.empty()) {
+        DEV(d_segs, sz_seg[0], b->segs.size() * sizeof(DevSeg));
+        DEV(d_seg_tasks, sz_seg[1], b->seg_tasks.size() * sizeof(SegTask));
+        DEV(d_seg_tables, sz_seg[2], b->seg_pages.size() * 4 + 16);
+        DEV(d_seg_work, sz_seg[3], b->seg_work.size() * 4 + 16);
+        DEV(d_seg_done, sz_seg[4], b->seg_tasks.size() * 4 + 16);
+        DEV(d_seg_foot, sz_seg[5], b->segs.size() * 4 + 16);
+        DEV(d_seg_rec, sz_seg[6], (size_t)b->seg_rec_total * sizeof(int4) + 16);
+        DEV(d_seg_snap, sz_seg[7], (size_t)b->seg_snap_words * 4 + 16);
+    }
 #undef DEV
     tr.lap("create: cudaMalloc");
     CKB(cudaMemsetAsync(b->d_timeline, 0, (n + 1) * 16, c->stream));
@@ -561,7 +639,13 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
     if (tbytes) CKB(cudaMemcpyAsync(b->d_t, tarena, tbytes, cudaMemcpyHostToDevice, c->stream));
     if (n) {
         CKB(cudaMemcpyAsync(b->d_tasks, b->tasks.data(), n * sizeof(DevTask), cudaMemcpyHostToDevice, c->stream));
-        CKB(cudaMemcpyAsync(b->d_work, b->work.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
+        if (!b->work.empty()) CKB(cudaMemcpyAsync(b->d_work, b->work.data(), b->work.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        if (!b->segs.empty()) {
+            CKB(cudaMemcpyAsync(b->d_segs, b->segs.data(), b->segs.size() * sizeof(DevSeg), cudaMemcpyHostToDevice, c->stream));
+            CKB(cudaMemcpyAsync(b->d_seg_tasks, b->seg_tasks.data(), b->seg_tasks.size() * sizeof(SegTask), cudaMemcpyHostToDevice, c->stream));
+            CKB(cudaMemcpyAsync(b->d_seg_tables, b->seg_pages.data(), b->seg_pages.size() * 4, cudaMemcpyHostToDevice, c->stream));
+            CKB(cudaMemcpyAsync(b->d_seg_work, b->seg_work.data(), b->seg_work.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        }
     }
     CKB(cudaStreamSynchronize(c->stream));
     tr.lap("create: H2D");
@@ -604,14 +688,24 @@ extern "C" int fsv_batch_run(fsv_batch* b)
     CK(c, cudaMemsetAsync(c->d_lazy, 0, sizeof(LazyState), c->stream));
     CK(c, cudaMemsetAsync(reinterpret_cast<uint8_t*>(c->d_lazy) + sizeof(LazyState), 0xff, (size_t)(n_slots + 1) * 4, c->stream));
     {   // control block: overflow flag, pool lock, free count, queue states; free stack = every page
+        const int64_t dyn_pages = b->pool_pages - b->seg_static_pages;      // segmented tasks own the top of the pool
         std::vector<int32_t> stack((size_t)b->pool_pages + 1);
-        for (int64_t i = 0; i < b->pool_pages; ++i) stack[(size_t)i] = (int32_t)i;
+        for (int64_t i = 0; i < dyn_pages; ++i) stack[(size_t)i] = (int32_t)i;
         CK(c, cudaMemcpyAsync(c->d_free_stack, stack.data(), (size_t)(b->pool_pages + 1) * 4, cudaMemcpyHostToDevice, c->stream));
         int32_t ctrl[128] = {0};
-        ctrl[2] = (int32_t)b->pool_pages;
+        ctrl[2] = (int32_t)dyn_pages;
         for (size_t i = 0; i < b->launches.size(); ++i) {
             unsigned long long st = (unsigned long long)(unsigned)b->launches[i].count;    // head 0, tail count
             memcpy(&ctrl[8 + 2 * i], &st, 8);
+        }
+        for (size_t i = 0; i < b->seg_launches.size(); ++i) {
+            unsigned long long st = (unsigned long long)(unsigned)b->seg_launches[i].count;
+            memcpy(&ctrl[8 + 2 * (b->launches.size() + i)], &st, 8);
+        }
+        if (!b->segs.empty()) {
+            CK(c, cudaMemsetAsync(b->d_seg_done, 0, b->seg_tasks.size() * 4, c->stream));
+            CK(c, cudaMemsetAsync(b->d_seg_foot, 0xff, b->segs.size() * 4, c->stream));
+            CK(c, cudaMemsetAsync(b->d_seg_snap, 0, (size_t)b->seg_snap_words * 4, c->stream));
         }
         CK(c, cudaMemcpyAsync(b->d_ctrl, ctrl, sizeof ctrl, cudaMemcpyHostToDevice, c->stream));
         CK(c, cudaMemsetAsync(b->d_cursor, 0, 64, c->stream));
@@ -620,10 +714,10 @@ extern "C" int fsv_batch_run(fsv_batch* b)
     tr.lap("run: scratch + control block");
     RunCtx R{};
     R.qarena = b->d_q; R.tarena = b->d_t; R.tasks = b->d_tasks; R.results = b->d_results;
-    R.pool.base = c->d_pool; R.pool.page_bytes = c->page_bytes; R.pool.n_pages = (int32_t)b->pool_pages;
+    R.pool.base = c->d_pool; R.pool.page_bytes = c->page_bytes; R.pool.n_pages = (int32_t)(b->pool_pages - b->seg_static_pages);
     R.pool.free_stack = c->d_free_stack; R.pool.n_free = b->d_ctrl + 2; R.pool.lock = b->d_ctrl + 1; R.pool.progress = b->d_ctrl + 3; R.pool.gate = b->d_ctrl + 4;
     // lazy growth only pays (and only costs) when the batch's traceback does not fit the pool at once
-    const bool lazy_on = c->lazy_min_pages > 0 && b->pool_pages < b->pages_total;
+    const bool lazy_on = c->lazy_min_pages > 0 && b->pool_pages < b->pages_total;      // (static pages of segmented tasks count on both sides)
     R.pool.lazy = lazy_on ? reinterpret_cast<LazyState*>(c->d_lazy) : nullptr;
     R.pool.slot_idx = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(c->d_lazy) + sizeof(LazyState));
     R.pool.lazy_min_pages = lazy_on ? c->lazy_min_pages : 0;
@@ -634,14 +728,32 @@ extern "C" int fsv_batch_run(fsv_batch* b)
     R.cigar = b->d_cigar; R.cigar_cursor = b->d_cursor; R.cigar_cap = b->cigar_cap_words; R.overflow = b->d_ctrl + 0;
     R.timeline = b->d_timeline;
     R.sc = b->sc;
+    R.segs = b->d_segs; R.seg_tasks = b->d_seg_tasks; R.seg_rec = b->d_seg_rec; R.seg_snap = b->d_seg_snap;
+    R.seg_tables = b->d_seg_tables; R.seg_done = b->d_seg_done; R.seg_foot = b->d_seg_foot;
 
     cudaEvent_t e0, e1;
     CK(c, cudaEventCreate(&e0)); CK(c, cudaEventCreate(&e1));
-    std::vector<cudaEvent_t> done(b->launches.size());
+    std::vector<cudaEvent_t> done(b->launches.size() + b->seg_launches.size());
     CK(c, cudaEventRecord(e0, c->stream));
     // every kernel variant runs concurrently on its own stream; they share the page pool, so the long
     // tasks of one class overlap the short tasks of all the others
     int32_t slot_base = 0;
+    // segments of the long tasks first: they are what the batch waits for
+    for (size_t i = 0; i < b->seg_launches.size(); ++i) {
+        const auto& L = b->seg_launches[i];
+        const size_t qi = b->launches.size() + i;
+        cudaStream_t ks = c->kstream[qi] ? c->kstream[qi] : c->stream;
+        CK(c, cudaStreamWaitEvent(ks, e0, 0));
+        TaskQueue Q{reinterpret_cast<unsigned long long*>(b->d_ctrl + 8 + 2 * qi), b->d_seg_work + L.begin};
+        R.page_tables = c->d_tables; R.slot_base = 0;
+        DpxParams D{R, Q, DpxK{}};
+        rc = b->dual ? dpx_launch_seg_1(ks, c->sm_count, L.nw, L.count, D, &c->last_error) : dpx_launch_seg_0(ks, c->sm_count, L.nw, L.count, D, &c->last_error);
+        if (rc != FSV_OK) return rc;
+        c->stats.fill_launches++;
+        CK(c, cudaEventCreateWithFlags(&done[qi], cudaEventDisableTiming));
+        CK(c, cudaEventRecord(done[qi], ks));
+        CK(c, cudaStreamWaitEvent(c->stream, done[qi], 0));
+    }
     for (size_t i = 0; i < b->launches.size(); ++i) {
         const Launch& L = b->launches[i];
         cudaStream_t ks = c->kstream[i] ? c->kstream[i] : c->stream;

@@ -31,7 +31,7 @@ struct DevTask {
     int32_t tb_pages;       // traceback pages this task needs (0 = score only)
     int32_t rows_per_page;  // antidiagonals per page
     int32_t wild;           // some base of the task is the wildcard (code > 3)
-    int32_t pad2_;
+    int32_t seg_id;         // index into RunCtx::seg_tasks when the task is cut into segments, else -1
 };
 
 // where the CIGAR walk of a task starts (ksw2_extz2_sse.c:292-301)
@@ -287,6 +287,31 @@ __device__ inline int queue_take(const TaskQueue& Q, int end)
     }
 }
 
+// ---------------------------------------------------------------------------
+// Segmented tasks.  The difference recurrence forgets its start after about 2w antidiagonals (DESIGN.md section 6,
+// scripts/convergence_probe.py), so a long task is cut into segments of whole traceback pages that run on
+// different CTAs at the same time: segment s > 0 starts COLD `warm` antidiagonals before its first own row, writes
+// traceback rows and one record per antidiagonal from its first own row on, and dumps its state at its first and
+// last own rows.  The CTA that finishes the task's last segment checks every boundary bit for bit (the state a
+// segment reached cold == the state its predecessor reached from the truth), chains the score offsets, replays the
+// ksw_extz_t bookkeeping over the records and walks the CIGAR; any mismatch re-runs the task unsegmented.
+struct DevSeg {
+    int32_t task;               // index into tasks[]
+    int32_t index, count;       // this segment, segments of the task
+    int32_t r0;                 // first antidiagonal computed (cold start; 0 for segment 0)
+    int32_t r_begin, r_end;     // antidiagonals this segment owns: [r_begin, r_end)
+};
+struct SegTask {
+    int64_t rec_off;            // into seg_rec: one int4 per antidiagonal {max H, argmax column, H[en0] | NEG_INF, H[st0] | NEG_INF}
+    int64_t snap_off;           // into seg_snap (words): boundary b = slots 2b (last row of segment b) and 2b+1 (warm end of b+1)
+    int32_t table_off;          // into seg_tables: the task's page table (static pages, all rows)
+    int32_t n_segs, first_seg;
+    int32_t pad_;
+};
+constexpr int SEG_SNAP_HDR = 8;                 // words: anchor H (lane st0), valid flag
+constexpr int SEG_SNAP_PER_THREAD = 67;         // 64 state words, Vt, Hb, reserved
+constexpr int SEG_SNAP_WORDS = SEG_SNAP_HDR + 256 * SEG_SNAP_PER_THREAD;
+
 // everything a fill kernel needs besides its own parameters
 struct RunCtx {
     const uint8_t* qarena;
@@ -303,6 +328,14 @@ struct RunCtx {
     int32_t* overflow;           // set when the arena is too small
     long long* timeline;         // per task (caller order): start ns, end ns (globaltimer), or null
     DevScoring sc;
+    // segmented tasks (null / unused when the batch has none)
+    const DevSeg* segs;
+    const SegTask* seg_tasks;
+    int4* seg_rec;
+    uint32_t* seg_snap;
+    const int32_t* seg_tables;
+    int32_t* seg_done;           // per segmented task: segments finished
+    int32_t* seg_foot;           // per segment: antidiagonal at which the band ran out inside it, or -1
 };
 
 __device__ __forceinline__ long long global_ns()

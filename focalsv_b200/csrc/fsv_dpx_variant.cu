@@ -24,4 +24,11 @@ int FSV_CAT3(dpx_launch_, FSV_VARIANT_DUAL, FSV_VARIANT_TBM)(cudaStream_t stream
     return dpx_launch_nw<FSV_VARIANT_DUAL != 0, FSV_VARIANT_TBM>(stream, nw, grid, excl, P, err);
 }
 
+#if FSV_VARIANT_TBM == 1
+int FSV_CAT3(dpx_launch_seg_, FSV_VARIANT_DUAL, )(cudaStream_t stream, int sm_count, int nw, int n_segs, const DpxParams& P, std::string* err)
+{
+    return dpx_launch_seg_nw<FSV_VARIANT_DUAL != 0>(stream, sm_count, nw, n_segs, P, err);
+}
+#endif
+
 }  // namespace fsv

@@ -230,7 +230,8 @@ __device__ __forceinline__ void dpx_cells(uint32_t (&U)[8], uint32_t (&V)[8], ui
 // shared memory reserved, so that a CTA working on one of the few very long tasks has its SM to itself.
 // TBM: 0 = score only, 1 = traceback, ties to the left (default), 2 = traceback, ties to the right (KSW_EZ_RIGHT),
 // 3 = score only with KSW_EZ_APPROX_MAX (:270-286): no H[] at all, one cell is followed greedily.
-template <bool DUAL, int TBM, int NW, bool EXCL = false>
+// SEG: the launch works on SEGMENTS of long tasks (fsv_common.cuh, DevSeg): P.Q holds segment indices.
+template <bool DUAL, int TBM, int NW, bool EXCL = false, bool SEG = false>
 __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kernel(const __grid_constant__ DpxParams P)
 {
     constexpr int NT = NW * 32;
@@ -242,7 +243,8 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
     //   traceback pages the task holds (thread 0's; fewer than tb_pages = a lazily growing task);
     //   APPROX: v[t*] and u[t*+1] of the followed cell, by antidiagonal parity
     constexpr uint32_t OFF_EDGE = 0, OFF_MH = 2 * NW * 32, OFF_KEY = OFF_MH + 3 * NW * 4, OFF_HEN0 = OFF_KEY + 12,
-                       OFF_HST0 = OFF_HEN0 + 12, OFF_STOP = OFF_HST0 + 12, OFF_TASK = OFF_STOP + 4, OFF_HELD = OFF_TASK + 4, OFF_APV = OFF_HELD + 4, OFF_APU = OFF_APV + 8, SH_BYTES = OFF_APU + 8;
+                       OFF_HST0 = OFF_HEN0 + 12, OFF_STOP = OFF_HST0 + 12, OFF_TASK = OFF_STOP + 4, OFF_HELD = OFF_TASK + 4, OFF_APV = OFF_HELD + 4, OFF_APU = OFF_APV + 8, OFF_SEG = OFF_APU + 8, OFF_SCAN = OFF_SEG + 8,
+                       SH_BYTES = OFF_SCAN + (SEG ? 4 * NW + 4 * NT : 0);      // SEG: scratch of the H re-anchoring scan
     __shared__ __align__(16) uint32_t sh_raw[(SH_BYTES + 15) / 16 * 4];
     uint32_t sb = (uint32_t)__cvta_generic_to_shared(sh_raw);
     const RunCtx& C = P.C;
@@ -258,25 +260,35 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
     const uint32_t extSel = DUAL ? 0xB391u : 0x4341u;                  // int8 (signed / unsigned) -> int16
     int32_t* table = C.page_tables + (int64_t)blockIdx.x * C.max_pages_per_task;
     int pending = -1;
+    int seg_redo = -1;          // SEG: segment index whose task failed the boundary check and is re-run whole by this CTA
 
     for (;;) {
         __syncthreads();
         if (tid == 0) {
             int held = 0;
-            sts32(sb + OFF_TASK, (uint32_t)next_task(C, P.Q, table, pending, true, held));
+            if (SEG) sts32(sb + OFF_TASK, (uint32_t)(seg_redo >= 0 ? seg_redo : queue_take(P.Q, 0)));
+            else sts32(sb + OFF_TASK, (uint32_t)next_task(C, P.Q, table, pending, true, held));
             sts32(sb + OFF_STOP, (uint32_t)INT32_MAX); sts32(sb + OFF_HELD, (uint32_t)held);
         }
         __syncthreads();
-        const int ti = (int)lds32(sb + OFF_TASK);
-        if (ti < 0) return;
+        const int wi = (int)lds32(sb + OFF_TASK);      // task index, or (SEG) segment index
+        if (wi < 0) return;
+        // a segment of a long task, or (seg_redo) the whole task again on its static page table
+        DevSeg G{wi, 0, 1, 0, 0, 0};
+        if (SEG) G = C.segs[wi];
+        const int ti = G.task;
         const DevTask T = C.tasks[ti];
-        if (tid == 0 && C.timeline) C.timeline[2 * T.orig] = global_ns();
+        const bool segmode = SEG && seg_redo < 0;
+        if (SEG) { table = const_cast<int32_t*>(C.seg_tables) + C.seg_tasks[T.seg_id].table_off; seg_redo = -1; }
+        const int rz = segmode ? G.r0 : 0;                                 // first antidiagonal computed
+        const int r_own = segmode ? G.r_begin : 0;                         // first antidiagonal whose results count
+        if (tid == 0 && C.timeline && (!SEG || G.index == 0)) C.timeline[2 * T.orig] = global_ns();
         const int qlen = T.qlen, tlen = T.tlen, w = T.w;
         const uint8_t* query = C.qarena + T.q_off;
         const uint8_t* target = C.tarena + T.t_off;
         // traceback rows live in pool pages: row r is in page r / rows_per_page
-        int tb_rip = 0, tb_pg = 0;                 // row inside the current page, page number
-        uint8_t* tb_page = TB ? C.pool.base + (int64_t)table[0] * C.pool.page_bytes : nullptr;
+        int tb_rip = 0, tb_pg = SEG ? r_own / T.rows_per_page : 0;     // row inside the current page, page number (segments own whole pages)
+        uint8_t* tb_page = TB ? C.pool.base + (int64_t)table[tb_pg] * C.pool.page_bytes : nullptr;
         const int n_diag = qlen + tlen - 1;
 
         uint32_t U[8], V[8], X[8], Y[8], X2[8], Y2[8], S[8], Hr[8];
@@ -294,7 +306,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
         // The ksw_extz_t bookkeeping of antidiagonal d is finished two iterations later (d+2), by warp 0
         // only: the maximum of d crosses the CTA through shared memory behind the ONE barrier of
         // iteration d, the tie-break key of the lanes holding it behind the barrier of iteration d+1.
-        int stop_r = n_diag;        // first antidiagonal that is not computed (band exhausted, :111)
+        int stop_r = segmode ? G.r_end : n_diag;        // first antidiagonal that is not computed (band exhausted, :111; end of the segment)
         bool dropped = false;
         int32_t maxrun = 0;         // ez.max as every warp can track it (running maximum, ksw2.h:164)
         int32_t M1 = 0, M2 = 0;     // max H of antidiagonals r-1, r-2
@@ -307,7 +319,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
         // left to itself the compiler predicates the `if (wild)` blocks, and predicated-off instructions still issue.
         auto fill_loop = [&](auto wild_c) {
         constexpr bool wild = decltype(wild_c)::value;
-        for (int r = 0;; ++r) {
+        for (int r = rz;; ++r) {
             const int par = r & 1, ppar = par ^ 1;
             const int s3m1 = s3 == 0 ? 2 : s3 - 1, s3m2 = s3 == 2 ? 0 : s3 + 1;   // (r-1)%3, (r-2)%3
 
@@ -319,14 +331,14 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
             if (wild) {
                 nbA = __shfl_up_sync(FULL, amb, 1);
                 if (NW == 1) { const uint32_t a2 = __shfl_sync(FULL, amb, 31); if (lane == 0) nbA = a2; }
-                else if (lane == 0 && r > 0) nbA = lds32(sb + OFF_EDGE + (uint32_t)(ppar * NW + (warp + NW - 1) % NW) * 32u + 20u);
+                else if (lane == 0 && r > rz) nbA = lds32(sb + OFF_EDGE + (uint32_t)(ppar * NW + (warp + NW - 1) % NW) * 32u + 20u);
                 nbA = (nbA >> 15) & 1u;
             }
             if (NW == 1) {
                 uint32_t a = __shfl_sync(FULL, X[7], 31), b = __shfl_sync(FULL, V[7], 31);
                 uint32_t c2 = DUAL ? __shfl_sync(FULL, X2[7], 31) : 0, q2 = __shfl_sync(FULL, qw, 31);
                 if (lane == 0) { nbX = a; nbV = b; nbX2 = c2; nbQ = q2; }
-            } else if (lane == 0 && r > 0) {
+            } else if (lane == 0 && r > rz) {
                 const int pw = (warp + NW - 1) % NW;
                 const uint4 e = lds128(sb + OFF_EDGE + (uint32_t)(ppar * NW + pw) * 32u);
                 nbX = e.x; nbV = e.y; nbX2 = e.z; nbQ = e.w;
@@ -355,10 +367,24 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                 }
             }
             // ---- (A) antidiagonal d = r-2 is final: bookkeeping (ksw2_extz2_sse.c:262-269)
-            if (!APPROX && r >= 2) {
+            if (!APPROX && r >= rz + 2) {
                 if ((int)lds32(sb + OFF_STOP) < r) { dropped = true; break; }      // set during an EARLIER iteration: every thread agrees
                 maxrun = max(maxrun, M2);
                 const int d = r - 2;
+                if (SEG && segmode) {
+                    // a segment only RECORDS its own antidiagonals (scores relative to its own cold start): the
+                    // bookkeeping is replayed over the whole task once every boundary has been checked
+                    if (warp == 0 && lane == 0 && d >= r_own) {
+                        int st0d, en0d;
+                        band_limits(d, qlen, tlen, w, st0d, en0d);
+                        int max_t = en0d;
+                        const uint32_t bk = lds32(sb + OFF_KEY + 4u * s3m2);
+                        if (bk != 0) max_t = (int)((bk - 1u) & ((1u << 26) - 1u));
+                        const int32_t hen0 = en0d == tlen - 1 ? (int32_t)lds32(sb + OFF_HEN0 + 4u * s3m2) : FSV_NEG_INF;
+                        const int32_t hst0 = d - st0d == qlen - 1 ? (int32_t)lds32(sb + OFF_HST0 + 4u * s3m2) : FSV_NEG_INF;
+                        C.seg_rec[C.seg_tasks[T.seg_id].rec_off + d] = make_int4(M2, max_t, hen0, hst0);
+                    }
+                } else
                 if (warp == 0 && !dropped) {
                     int st0d, en0d;
                     band_limits(d, qlen, tlen, w, st0d, en0d);
@@ -387,11 +413,11 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                 }
             }
             // ---- (B) antidiagonal r-1: its maximum, and (only if observable, ksw2.h:164-174) who holds it
-            if (!APPROX && r >= 1 && r - 1 < stop_r) {
+            if (!APPROX && r >= rz + 1 && r - 1 < stop_r) {
                 const int32_t m = __reduce_max_sync(FULL, lane < NW ? (int32_t)lds32(sb + OFF_MH + 4u * (uint32_t)(s3m1 * NW + lane)) : INT32_MIN);
                 M1 = m;
                 const int32_t mr = max(maxrun, M2);      // ez.max once r-2 is accounted for
-                nt1 = m > mr || (T.zdrop >= 0 && mr - m > T.zdrop);
+                nt1 = m > mr || (T.zdrop >= 0 && mr - m > T.zdrop) || (SEG && segmode);      // a segment cannot know: always
                 if (nt1 && act_p && habs_p == m) {
                     // lanes of this vector that hold the maximum, as a 16-bit mask
                     const int base = Vt << 4;
@@ -450,7 +476,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                     const uint32_t X2T0 = DUAL ? prmt(nbX2, X2[7], 0x5432u) : 0;
                     uint4 o;
                     dpx_cells<DUAL, TB, RIGHT>(U, V, X, Y, X2, Y2, S, XT0, VT0, X2T0, K, o);
-                    if (TB) *reinterpret_cast<uint4*>(tb_page + (int64_t)tb_rip * T.pitch + (base - st)) = o;
+                    if (TB && (!SEG || r >= r_own)) *reinterpret_cast<uint4*>(tb_page + (int64_t)tb_rip * T.pitch + (base - st)) = o;
                     if (APPROX) approx_post(base);
                     else {
 #pragma unroll
@@ -476,7 +502,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                     if (!APPROX) nbH = __shfl_up_sync(FULL, Hb + sext16(Hr[7] >> 16), 1);
                     if (APPROX) {}
                     else if (NW == 1) { int32_t h = __shfl_sync(FULL, Hb + sext16(Hr[7] >> 16), 31); if (lane == 0) nbH = h; }
-                    else if (lane == 0 && r > 0) nbH = (int32_t)lds32(sb + OFF_EDGE + (uint32_t)(ppar * NW + (warp + NW - 1) % NW) * 32u + 16u);
+                    else if (lane == 0 && r > rz) nbH = (int32_t)lds32(sb + OFF_EDGE + (uint32_t)(ppar * NW + (warp + NW - 1) % NW) * 32u + 16u);
                     bool rearmed = false;
                     if (Vt < st_) {            // a vector that fell below the band re-arms NT vectors to the right
                         Vt += NT;
@@ -484,6 +510,15 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                         rearmed = true;
 #pragma unroll
                         for (int k = 0; k < 8; ++k) { U[k] = K.gU; V[k] = K.gU; X[k] = K.gX; Y[k] = K.gY; X2[k] = K.gX2; Y2[k] = K.gY2; S[k] = K.sInit; Hr[k] = 0; }
+                        if (SEG && segmode && rz > 0 && r == rz && Vt <= en_) {
+                            // cold start of a segment: the reference's initial constants describe a surface that falls by q+e
+                            // per lane, a cliff against the true one that the clamp lets erode only slowly; start FLAT
+                            // instead (u = v = 0) so that the true diagonal takes over like a seed and the gap regimes
+                            // spread from it at one lane per antidiagonal
+                            const uint32_t flat = both(DUAL ? 0u : hi8(K.qe));
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) { U[k] = flat; V[k] = flat; }
+                        }
                         Hb = 0;
                         tw = 0; qw = 0; amb = 0;
                         const int nb = Vt << 4;
@@ -562,7 +597,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
 
                         uint4 o;
                         dpx_cells<DUAL, TB, RIGHT>(U, V, X, Y, X2, Y2, S, XT0, VT0, X2T0, K, o);
-                        if (TB) *reinterpret_cast<uint4*>(tb_page + (int64_t)tb_rip * T.pitch + (base - st)) = o;
+                        if (TB && (!SEG || r >= r_own)) *reinterpret_cast<uint4*>(tb_page + (int64_t)tb_rip * T.pitch + (base - st)) = o;
                         if (APPROX) approx_post(base);
                         else {
                         // exact max bookkeeping (:224-260): H[t] += v[t] - qe ; H[en0] from its left neighbour
@@ -606,6 +641,50 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                     }
                 }
                 habs_p = habs; st0p = st0; en0p = en0;
+                if (SEG && segmode && G.index > 0 && r == r_own - 1) {
+                    // End of the warm-up: the difference arrays have converged to the truth, the tracked H has not
+                    // (every lane started from its own zero).  Rebuild it on this antidiagonal from ONE anchor, lane st0
+                    // := 0, with the identity the reference's own H updates keep exactly for neighbouring in-band lanes:
+                    // H[t] - H[t-1] = u[t] - v[t-1]  (:231,239-241).  From here on H is the truth minus one constant.
+                    uint32_t vprev = __shfl_up_sync(FULL, V[7], 1);
+                    if (NW > 1) {
+                        if (lane == 31) sts32(sb + OFF_SCAN + 4u * (uint32_t)warp, V[7]);
+                        __syncthreads();
+                        if (lane == 0) vprev = lds32(sb + OFF_SCAN + 4u * (uint32_t)((warp + NW - 1) % NW));
+                    } else { const uint32_t x = __shfl_sync(FULL, V[7], 31); if (lane == 0) vprev = x; }
+                    const int base = Vt << 4;
+                    int pre[16], run = 0;
+#pragma unroll
+                    for (int cc = 0; cc < 16; ++cc) {
+                        const uint32_t v16 = cc == 0 ? (vprev >> 16) : get_cell(V, cc - 1), u16 = get_cell(U, cc);
+                        const int vl = DUAL ? (int)(int8_t)(v16 >> 8) : (int)((v16 >> 8) & 0xffu), ul = DUAL ? (int)(int8_t)(u16 >> 8) : (int)((u16 >> 8) & 0xffu);
+                        const int t = base + cc;
+                        if (t > st0 && t <= en0) run += ul - vl;
+                        pre[cc] = run;
+                    }
+                    const int idx = min(max(Vt - st_, 0), NT - 1);               // position of this vector in the band
+                    sts32(sb + OFF_SCAN + 4u * NW + 4u * (uint32_t)idx, (uint32_t)run);
+                    __syncthreads();
+                    int off = 0;
+                    for (int k = 0; k < idx; ++k) off += (int)lds32(sb + OFF_SCAN + 4u * NW + 4u * (uint32_t)k);
+                    Hb = off;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) Hr[k] = ((uint32_t)pre[k] & 0xffffu) | ((uint32_t)pre[k + 8] << 16);
+                    __syncthreads();
+                }
+                if (SEG && segmode && ((r == r_own - 1 && G.index > 0) || (r == G.r_end - 1 && G.index + 1 < G.count))) {
+                    // state after this antidiagonal: the last own row (slot 2*index) or the end of the warm-up (2*(index-1)+1)
+                    const int slot = r == G.r_end - 1 ? 2 * G.index : 2 * (G.index - 1) + 1;
+                    uint32_t* sn = C.seg_snap + C.seg_tasks[T.seg_id].snap_off + (int64_t)slot * SEG_SNAP_WORDS;
+                    uint32_t* mine = sn + SEG_SNAP_HDR + tid;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        mine[(0 + k) * NT] = U[k]; mine[(8 + k) * NT] = V[k]; mine[(16 + k) * NT] = X[k]; mine[(24 + k) * NT] = Y[k];
+                        mine[(32 + k) * NT] = X2[k]; mine[(40 + k) * NT] = Y2[k]; mine[(48 + k) * NT] = S[k]; mine[(56 + k) * NT] = Hr[k];
+                    }
+                    mine[64 * NT] = (uint32_t)Vt; mine[65 * NT] = (uint32_t)Hb; mine[66 * NT] = (uint32_t)hprev_keep;
+                    if (Vt == st_) { sn[0] = (uint32_t)(Hb + sext16(get_cell(Hr, st0 - (Vt << 4)))); sn[1] = 1u; }     // anchor: H of lane st0
+                }
                 // lane 15 of every warp's last vector, for the next antidiagonal
                 if (NW > 1 && lane == 31) {
                     const uint32_t ea = sb + OFF_EDGE + (uint32_t)(par * NW + warp) * 32u;
@@ -617,11 +696,11 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                     const int32_t wmax = __reduce_max_sync(FULL, habs);
                     if (lane == 0) sts32(sb + OFF_MH + 4u * (uint32_t)(s3 * NW + warp), (uint32_t)wmax);
                 }
-                if (TB && ++tb_rip == T.rows_per_page) {
+                if (TB && (!SEG || r >= r_own) && ++tb_rip == T.rows_per_page) {
                     tb_rip = 0; ++tb_pg;
                     if (tb_pg < T.tb_pages) tb_page = C.pool.base + (int64_t)table[tb_pg] * C.pool.page_bytes;
                     // (thread 0 of a lazily growing task) one page ahead: the CTA reads table[tb_pg + 1] a whole page of antidiagonals from now
-                    if (tid == 0 && tb_pg + 1 < T.tb_pages) {
+                    if (!SEG && tid == 0 && tb_pg + 1 < T.tb_pages) {
                         const int held = (int)lds32(sb + OFF_HELD);
                         if (held < tb_pg + 2) sts32(sb + OFF_HELD, (uint32_t)pool_lazy_grow(C.pool, C.slot_base + (int)blockIdx.x, table, held, tb_pg + 2));
                     }
@@ -635,13 +714,123 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
         };
         if (wild_task) fill_loop(std::true_type{}); else fill_loop(std::false_type{});
         if (!dropped && stop_r < n_diag) ez.zdropped = 1;      // band exhausted (:111-114)
+        if (SEG && segmode) {
+            // ---- end of a segment; the CTA that finishes the task's last one stitches the task together
+            const SegTask ST = C.seg_tasks[T.seg_id];
+            __threadfence();                 // this thread's traceback rows, records and snapshot words
+            __syncthreads();
+            if (tid == 0) {
+                C.seg_foot[ST.first_seg + G.index] = stop_r < G.r_end ? stop_r : -1;      // the band ran out inside this segment
+                __threadfence();
+                sts32(sb + OFF_SEG, atomicAdd(&C.seg_done[T.seg_id], 1) == G.count - 1 ? 1u : 0u);
+            }
+            __syncthreads();
+            if (!lds32(sb + OFF_SEG)) continue;
+            __threadfence();
+            // (1) every boundary: the state segment b+1 reached from its cold start == the state segment b reached
+            bool bad = false;
+            for (int b = 0; b + 1 < G.count; ++b) {
+                if (((volatile int32_t*)C.seg_foot)[ST.first_seg + b] >= 0) break;       // the alignment ends inside segment b
+                const int rb = C.segs[ST.first_seg + b].r_end - 1;
+                int st0b, en0b;
+                band_limits(rb, qlen, tlen, w, st0b, en0b);
+                const int stv = round_st(st0b) >> 4, env = round_en(en0b) >> 4;
+                const uint32_t* A = C.seg_snap + ST.snap_off + (int64_t)(2 * b) * SEG_SNAP_WORDS;
+                const uint32_t* B = A + SEG_SNAP_WORDS;
+                if (__ldcg(A + 1) != 1u || __ldcg(B + 1) != 1u) bad = true;
+                const int32_t ancA = (int32_t)__ldcg(A), ancB = (int32_t)__ldcg(B);
+                const uint32_t* a = A + SEG_SNAP_HDR + tid; const uint32_t* bq = B + SEG_SNAP_HDR + tid;
+                const int va = (int)__ldcg(a + 64 * NT), vb = (int)__ldcg(bq + 64 * NT);
+                if (va != vb) bad = true;
+#ifdef FSV_SEG_DEBUG
+                if (va != vb && tid < 4) printf("seg dbg: task %d boundary %d tid %d Vt %d vs %d (valid %u %u anc %d %d)\n", T.orig, b, tid, va, vb, __ldcg(A + 1), __ldcg(B + 1), ancA, ancB);
+#endif
+                if (va >= stv) for (int k = 48; k < 56; ++k) if (__ldcg(a + k * NT) != __ldcg(bq + k * NT)) {
+                    bad = true;     // s, also of vectors above the band
+#ifdef FSV_SEG_DEBUG
+                    printf("seg dbg: task %d boundary %d rb %d tid %d Vt %d (band vectors %d..%d) S word %d: %08x vs %08x\n", T.orig, b, rb, tid, va, stv, env, k - 48, __ldcg(a + k * NT), __ldcg(bq + k * NT));
+#endif
+                }
+#ifdef FSV_SEG_DEBUG
+                if (b == 0 && va - stv >= 92 && va - stv <= 99) {
+                    for (int arr = 0; arr < 7; ++arr)
+                        printf("dump idx %d arr %d A %08x %08x %08x %08x %08x %08x %08x %08x | B %08x %08x %08x %08x %08x %08x %08x %08x\n", va - stv, arr,
+                               __ldcg(a + (arr*8+0) * NT), __ldcg(a + (arr*8+1) * NT), __ldcg(a + (arr*8+2) * NT), __ldcg(a + (arr*8+3) * NT), __ldcg(a + (arr*8+4) * NT), __ldcg(a + (arr*8+5) * NT), __ldcg(a + (arr*8+6) * NT), __ldcg(a + (arr*8+7) * NT),
+                               __ldcg(bq + (arr*8+0) * NT), __ldcg(bq + (arr*8+1) * NT), __ldcg(bq + (arr*8+2) * NT), __ldcg(bq + (arr*8+3) * NT), __ldcg(bq + (arr*8+4) * NT), __ldcg(bq + (arr*8+5) * NT), __ldcg(bq + (arr*8+6) * NT), __ldcg(bq + (arr*8+7) * NT));
+                }
+#endif
+                if (va >= stv && va <= env) {
+                    for (int k = 0; k < 48; ++k) if (__ldcg(a + k * NT) != __ldcg(bq + k * NT)) {
+                        bad = true;             // u v x y x2 y2
+#ifdef FSV_SEG_DEBUG
+                        if (k % 8 == 0) printf("seg dbg: task %d boundary %d rb %d tid %d Vt %d (band %d..%d) array %d word %d: %08x vs %08x\n", T.orig, b, rb, tid, va, stv, env, k / 8, k % 8, __ldcg(a + k * NT), __ldcg(bq + k * NT));
+#endif
+                    }
+                    const int32_t hba = (int32_t)__ldcg(a + 65 * NT), hbb = (int32_t)__ldcg(bq + 65 * NT);
+                    for (int c = 0; c < 16; ++c) {                                                                   // H relative to the anchor lane
+                        const int t = (va << 4) + c;
+                        if (t < st0b || t > en0b) continue;
+                        const uint32_t wa = __ldcg(a + (56 + (c & 7)) * NT), wb = __ldcg(bq + (56 + (c & 7)) * NT);
+                        const int32_t ha = hba + sext16(c & 8 ? wa >> 16 : wa) - ancA, hb = hbb + sext16(c & 8 ? wb >> 16 : wb) - ancB;
+                        if (ha != hb) {
+                            bad = true;
+#ifdef FSV_SEG_DEBUG
+                            if (c == 0) printf("seg dbg: task %d boundary %d tid %d Vt %d lane %d H %d vs %d\n", T.orig, b, tid, va, c, ha, hb);
+#endif
+                        }
+                    }
+                }
+            }
+            if (__syncthreads_or(bad)) { seg_redo = ST.first_seg; continue; }      // re-run the task whole (this CTA, static pages)
+            // (2) warp 0 replays the ksw_extz_t bookkeeping (:262-269) over the records, 32 at a time
+            if (warp == 0) {
+                EzState e2; e2.reset();
+                int64_t cells2 = 0;
+                int32_t delta = 0;
+                bool stop = false;
+                for (int sgi = 0; sgi < G.count && !stop; ++sgi) {
+                    const DevSeg Gs = C.segs[ST.first_seg + sgi];
+                    const int foot = ((volatile int32_t*)C.seg_foot)[ST.first_seg + sgi];
+                    const int end = foot >= 0 ? foot : Gs.r_end;
+                    for (int d0 = Gs.r_begin; d0 < end && !stop; d0 += 32) {
+                        int4 rec = make_int4(0, 0, 0, 0);
+                        if (d0 + lane < end) rec = __ldcg(C.seg_rec + ST.rec_off + d0 + lane);
+                        const int nrec = min(32, end - d0);
+                        for (int k = 0; k < nrec; ++k) {
+                            const int d = d0 + k;
+                            const int32_t M = __shfl_sync(FULL, rec.x, k) + delta;
+                            const int max_t = __shfl_sync(FULL, rec.y, k);
+                            int32_t hen0 = __shfl_sync(FULL, rec.z, k), hst0 = __shfl_sync(FULL, rec.w, k);
+                            int st0d, en0d;
+                            band_limits(d, qlen, tlen, w, st0d, en0d);
+                            cells2 += en0d - st0d + 1;
+                            if (hen0 != FSV_NEG_INF) hen0 += delta;
+                            if (hst0 != FSV_NEG_INF) hst0 += delta;
+                            if (en0d == tlen - 1 && hen0 > e2.mte) { e2.mte = hen0; e2.mte_q = d - round_en(en0d); }
+                            if (d - st0d == qlen - 1 && hst0 > e2.mqe) { e2.mqe = hst0; e2.mqe_t = st0d; }
+                            if (e2.apply_zdrop(M, d, max_t, T.zdrop, sc.e_drop)) { stop = true; break; }
+                            if (d == n_diag - 1 && en0d == tlen - 1) e2.score = hen0;
+                        }
+                    }
+                    if (!stop && foot >= 0) { e2.zdropped = 1; stop = true; }                     // band exhausted (:111-114)
+                    if (!stop && sgi + 1 < G.count) {
+                        const uint32_t* A = C.seg_snap + ST.snap_off + (int64_t)(2 * sgi) * SEG_SNAP_WORDS;
+                        delta += (int32_t)__ldcg(A) - (int32_t)__ldcg(A + SEG_SNAP_WORDS);
+                    }
+                }
+                finish_task(C, T, table, e2, cells2, TB);
+            }
+            __syncthreads();
+            if (tid == 0 && C.timeline) C.timeline[2 * T.orig + 1] = global_ns();
+            continue;
+        }
 
         __syncthreads();             // every traceback row is written
         if (warp == 0) finish_task(C, T, table, ez, cells, TB);
         __syncthreads();
         if (tid == 0) {
             const bool lazy = C.pool.lazy && C.pool.lazy_min_pages > 0 && T.tb_pages >= C.pool.lazy_min_pages;      // as task_pages decided
-            pool_free(C.pool, (int)lds32(sb + OFF_HELD), table, lazy ? C.slot_base + (int)blockIdx.x : -1);
+            if (!SEG) pool_free(C.pool, (int)lds32(sb + OFF_HELD), table, lazy ? C.slot_base + (int)blockIdx.x : -1);
             if (C.timeline) C.timeline[2 * T.orig + 1] = global_ns();
         }
     }
@@ -704,6 +893,33 @@ inline int dpx_launch_one(cudaStream_t stream, int grid, bool excl, const DpxPar
     return FSV_OK;
 }
 
+// segments of long tasks (TBM 1 only): persistent CTAs over the segment queue
+template <bool DUAL, int NW>
+inline int dpx_launch_seg_one(cudaStream_t stream, int sm_count, int n_segs, const DpxParams& P, std::string* err)
+{
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fsv_fill_dpx_kernel<DUAL, 1, NW, false, true>, NW * 32, 0) != cudaSuccess) { cudaGetLastError(); per_sm = 1; }
+    const int grid = std::max(1, std::min(n_segs, sm_count * std::max(per_sm, 1)));
+    DpxParams PK = P;
+    PK.K = DpxConst<DUAL, false>(P.C.sc);
+    fsv_fill_dpx_kernel<DUAL, 1, NW, false, true><<<grid, NW * 32, 0, stream>>>(PK);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { if (err) *err = cudaGetErrorString(e); return FSV_ERR_CUDA; }
+    return FSV_OK;
+}
+template <bool DUAL>
+inline int dpx_launch_seg_nw(cudaStream_t stream, int sm_count, int nw, int n_segs, const DpxParams& P, std::string* err)
+{
+    switch (nw) {
+        case 1: return dpx_launch_seg_one<DUAL, 1>(stream, sm_count, n_segs, P, err);
+        case 2: return dpx_launch_seg_one<DUAL, 2>(stream, sm_count, n_segs, P, err);
+        case 4: return dpx_launch_seg_one<DUAL, 4>(stream, sm_count, n_segs, P, err);
+        case 6: return dpx_launch_seg_one<DUAL, 6>(stream, sm_count, n_segs, P, err);
+        case 8: return dpx_launch_seg_one<DUAL, 8>(stream, sm_count, n_segs, P, err);
+    }
+    return FSV_ERR_INVALID;
+}
+
 #define FSV_DPX_DISPATCH(CALL)                                                    \
     switch (nw) {                                                                 \
         case 1: return CALL(1);                                                   \
@@ -735,6 +951,8 @@ inline int dpx_launch_nw(cudaStream_t stream, int nw, int grid, bool excl, const
 #define FSV_DPX_FAMILY(D, T)                                                                                           \
     int dpx_grid_##D##T(int sm_count, int nw, int n_tasks);                                                           \
     int dpx_launch_##D##T(cudaStream_t stream, int nw, int grid, bool excl, const DpxParams& P, std::string* err);
+int dpx_launch_seg_0(cudaStream_t stream, int sm_count, int nw, int n_segs, const DpxParams& P, std::string* err);
+int dpx_launch_seg_1(cudaStream_t stream, int sm_count, int nw, int n_segs, const DpxParams& P, std::string* err);
 FSV_DPX_FAMILY(0, 0) FSV_DPX_FAMILY(0, 1) FSV_DPX_FAMILY(0, 2) FSV_DPX_FAMILY(0, 3) FSV_DPX_FAMILY(1, 0) FSV_DPX_FAMILY(1, 1) FSV_DPX_FAMILY(1, 2) FSV_DPX_FAMILY(1, 3)
 #undef FSV_DPX_FAMILY
 
