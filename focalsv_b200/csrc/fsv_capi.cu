@@ -54,8 +54,10 @@ struct fsv_ctx {
     int force_excl = 0;         // experiment: every DPX task on the exclusive (one CTA per SM) launch
     int exact_smem_lanes = 4096;
     int64_t page_bytes = 32ll << 20;
-    int64_t segment_min_diags = 0;   // tasks with at least this many antidiagonals are cut into segments (0 = off)
-    int64_t segment_rows = 65536;    // target antidiagonals per segment (rounded up to whole traceback pages)
+    int64_t segment_min_diags = -1;  // tasks with at least this many antidiagonals are cut into segments (0 = off, -1 = auto:
+                                     // those whose chain of antidiagonals would outlast 60 % of the batch's throughput time)
+    int segment_pool_pct = 45;       // share of the traceback pool the segmented tasks' static pages may take
+    int64_t segment_rows = 0;        // target antidiagonals per segment, rounded up to whole traceback pages (0 = auto: 4 x warm-up)
     int lazy_min_pages = 16;    // DPX tasks with at least this many traceback pages take them as they advance (0 = all up front)
     int pool_stall_ms = 60000;  // lazy-pool watchdog
     int lazy_fill_pct = 65;     // admission of such a task waits while the projected peak of those running exceeds this share of the pool
@@ -242,8 +244,9 @@ extern "C" int fsv_set_option(fsv_ctx* c, const char* key, int64_t value)
         if (value < 0 || value > (1 << 20)) return FSV_ERR_INVALID;
         c->lazy_min_pages = value == 0 ? 0 : (int)std::max<int64_t>(value, 3); return FSV_OK;
     }
-    if (!strcmp(key, "segment_min_diags")) { if (value < 0) return FSV_ERR_INVALID; c->segment_min_diags = value; return FSV_OK; }
-    if (!strcmp(key, "segment_rows")) { if (value < 1024) return FSV_ERR_INVALID; c->segment_rows = value; return FSV_OK; }
+    if (!strcmp(key, "segment_min_diags")) { if (value < -1) return FSV_ERR_INVALID; c->segment_min_diags = value; return FSV_OK; }
+    if (!strcmp(key, "segment_pool_pct")) { if (value < 1 || value > 90) return FSV_ERR_INVALID; c->segment_pool_pct = (int)value; return FSV_OK; }
+    if (!strcmp(key, "segment_rows")) { if (value != 0 && value < 1024) return FSV_ERR_INVALID; c->segment_rows = value; return FSV_OK; }
     if (!strcmp(key, "pool_stall_ms")) { if (value < 100) return FSV_ERR_INVALID; c->pool_stall_ms = (int)value; return FSV_OK; }
     if (!strcmp(key, "lazy_fill_pct")) {
         if (value < 1 || value > 100) return FSV_ERR_INVALID;
@@ -493,12 +496,26 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
     // ---- segmented tasks (fsv_common.cuh, DevSeg): the longest left-aligned CIGAR tasks are cut into segments of whole
     // traceback pages; their pages are static (taken from the top of the pool), at most 45 % of it
     std::vector<uint8_t> is_seg(n, 0);
-    if (c->segment_min_diags > 0) {
+    if (c->segment_min_diags != 0) {
+        // auto: the batch's throughput time if every SM were full (SM-seconds model of the exclusive planning below);
+        // a task whose own chain would outlast 60 % of it (or of 20 ms) is worth cutting up
+        int64_t min_diags = c->segment_min_diags;
+        if (min_diags < 0) {
+            double W = 0;
+            for (size_t i = 0; i < n; ++i) if (b->is_dpx[i]) {
+                const int nw = b->tasks[i].nw;
+                W += (double)(b->tasks[i].qlen + b->tasks[i].tlen) * (nw <= 2 ? 2.0e-6 : nw == 4 ? 1.8e-6 : 1.55e-6) / (nw == 1 ? 12.0 : nw == 2 ? 6.0 : nw == 4 ? 3.0 : 2.0);
+            }
+            const double t_thr = std::max(W / c->sm_count, 0.020);
+            min_diags = (int64_t)(0.6 * t_thr / 1.55e-6);
+        }
         std::vector<int32_t> by_len;
         for (size_t i = 0; i < n; ++i) {
             const DevTask& d = b->tasks[i];
             if (b->is_dpx[i] && d.tb_pages > 0 && !(d.flag & (FSV_EZ_RIGHT | FSV_EZ_SCORE_ONLY | FSV_EZ_APPROX_MAX)) && d.w >= 64 &&
-                (int64_t)d.qlen + d.tlen - 1 >= c->segment_min_diags) by_len.push_back((int32_t)i);
+                (int64_t)d.qlen + d.tlen - 1 >= min_diags &&
+                !(c->segment_min_diags < 0 && (d.flag & FSV_EZ_EXTZ_ONLY)))      // auto: extensions usually end early by z-drop, a segmented task cannot
+                by_len.push_back((int32_t)i);
         }
         std::stable_sort(by_len.begin(), by_len.end(), [&](int32_t a, int32_t x) { return b->tasks[a].qlen + b->tasks[a].tlen > b->tasks[x].qlen + b->tasks[x].tlen; });
         std::vector<std::vector<int32_t>> per_nw(9);
@@ -506,11 +523,15 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
             DevTask& d = b->tasks[(size_t)ti];
             const int64_t n_diag = (int64_t)d.qlen + d.tlen - 1;
             const int64_t rpp = d.rows_per_page;
-            const int64_t seg_rows = std::max<int64_t>(1, (c->segment_rows + rpp - 1) / rpp) * rpp;      // whole pages
-            const int64_t warm = 5ll * d.w + 1024;                    // measured: the whole band is bit-identical about 4w antidiagonals after a cold start
+            const int64_t warm = 5ll * d.w + 1024;                    // generous: a flat cold start is bit-identical well within it (fallback if not)
+            const int64_t want = c->segment_rows > 0 ? c->segment_rows : std::max<int64_t>(4 * warm, 16384);
+            const int64_t seg_rows = std::max<int64_t>(1, (want + rpp - 1) / rpp) * rpp;      // whole pages
             const int n_segs = (int)((n_diag + seg_rows - 1) / seg_rows);
             if (n_segs < 2 || seg_rows < 2 * warm) continue;
-            if ((b->seg_static_pages + d.tb_pages) * 100 > b->cap_pages * 45) continue;
+            // static pages: a share of the pool; smaller when the batch's traceback does not fit the pool anyway (then the
+            // pool, not the longest chain, is what the batch waits for: measured on cfg2, 25 % is neutral, 45 % costs 14 %)
+            const int pct = b->pages_total > b->cap_pages ? std::min(c->segment_pool_pct, 25) : c->segment_pool_pct;
+            if ((b->seg_static_pages + d.tb_pages) * 100 > b->cap_pages * pct) continue;
             SegTask st{};
             st.rec_off = b->seg_rec_total; st.snap_off = b->seg_snap_words; st.table_off = (int32_t)b->seg_pages.size();
             st.n_segs = n_segs; st.first_seg = (int32_t)b->segs.size();

@@ -821,7 +821,10 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                 finish_task(C, T, table, e2, cells2, TB);
             }
             __syncthreads();
-            if (tid == 0 && C.timeline) C.timeline[2 * T.orig + 1] = global_ns();
+            if (tid == 0) {
+                pool_free(C.pool, T.tb_pages, table);      // the task's static pages join the dynamic pool
+                if (C.timeline) C.timeline[2 * T.orig + 1] = global_ns();
+            }
             continue;
         }
 
@@ -831,6 +834,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
         if (tid == 0) {
             const bool lazy = C.pool.lazy && C.pool.lazy_min_pages > 0 && T.tb_pages >= C.pool.lazy_min_pages;      // as task_pages decided
             if (!SEG) pool_free(C.pool, (int)lds32(sb + OFF_HELD), table, lazy ? C.slot_base + (int)blockIdx.x : -1);
+            else pool_free(C.pool, T.tb_pages, table);      // (re-run of a segmented task) its static pages join the dynamic pool
             if (C.timeline) C.timeline[2 * T.orig + 1] = global_ns();
         }
     }

@@ -8,7 +8,7 @@ preset = sys.argv[1] if len(sys.argv) > 1 else "asm5"
 L = int(sys.argv[2]) if len(sys.argv) > 2 else 150000
 w = int(sys.argv[3]) if len(sys.argv) > 3 else 3001
 n = int(sys.argv[4]) if len(sys.argv) > 4 else 4
-seg_rows = int(sys.argv[5]) if len(sys.argv) > 5 else 65536
+seg_rows = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 flag = int(sys.argv[6], 0) if len(sys.argv) > 6 else 0
 rng = np.random.default_rng(11)
 pairs = []
