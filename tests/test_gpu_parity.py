@@ -328,6 +328,47 @@ def test_approximate_maximum_score_only_on_the_dpx_kernel(oracle, aligner, prese
     assert int(gres["zdropped"].sum()) >= 1 and all(int(x) == _abi.NEG_INF for x in gres["mqe"])
 
 
+@pytest.mark.parametrize("preset,w", [("hifiasm", 500), ("asm5", 3001)])
+def test_segmented_long_tasks(oracle, preset, w):
+    """Long tasks cut into cold-started segments that run on different CTAs (fsv_common.cuh, DevSeg): every field and
+    CIGAR word equals the oracle's, whether the boundary check passes (mutated sequences), fails and falls back to the
+    whole task (identical sequences keep a cold-start artefact), the alignment z-drops inside a later segment, or
+    short tasks share the batch."""
+    from focalsv_b200 import api
+    from focalsv_b200.presets import PRESETS
+    rng = np.random.default_rng(808 + w)
+    L = 70000
+    pairs, flags = [], []
+    ref = synth.random_seq(rng, L)
+    q, _ = synth.plant_svs(rng, ref, 5, max_net=min(w // 2 - 50, 1200), max_len=min(w // 2 - 60, 1000))
+    pairs.append((synth.mutate(rng, q, 0.001, 0.0003, 0.0003), ref)); flags.append(0)
+    ref = synth.random_seq(rng, L + 3000)
+    pairs.append((ref.copy(), ref)); flags.append(0)                                          # identical: fallback path
+    ref = synth.random_seq(rng, L)
+    q = synth.mutate(rng, ref, 0.001, 0.0003, 0.0003)
+    q = np.concatenate([q[: 2 * L // 3], synth.random_seq(rng, L // 3)])                      # diverges at 2/3: z-drop in a later segment
+    pairs.append((q, ref)); flags.append(0)
+    ref = synth.random_seq(rng, L)
+    pairs.append((synth.mutate(rng, ref, 0.002, 0.001, 0.001), ref)); flags.append(_abi.EZ_EXTZ_ONLY | _abi.EZ_REV_CIGAR)
+    for Ls in (300, 2500, 9000):                                                              # short company
+        ref = synth.random_seq(rng, Ls)
+        pairs.append((synth.mutate(rng, ref, 0.01, 0.004, 0.004), ref)); flags.append(0)
+    g = synth._pack("seg." + preset, preset, pairs, w, PRESETS[preset].zdrop, flags=np.array(flags, dtype=np.int32))
+    al = api.Aligner(0)
+    try:
+        al.set_option("segment_min_diags", 50000)          # force: every long task is segmented, extensions included
+        bad, ores, gres = compare_group(oracle, al, g, threads=16)
+        assert not bad, bad
+        assert int(gres["zdropped"][2]) == 1
+        launches_seg = al.stats()["fill_launches"]
+        al.set_option("segment_min_diags", 0)               # and the same batch unsegmented
+        bad, _, _ = compare_group(oracle, al, g, threads=16)
+        assert not bad, bad
+        assert al.stats()["fill_launches"] - launches_seg < launches_seg      # the segmented run had the extra segment launch
+    finally:
+        al.close()
+
+
 def test_mixed_kernel_variants_share_the_pool(oracle, aligner):
     """One batch whose tasks land on several kernel variants at once (1/2/4-warp DPX classes, score-only and
     CIGAR, wildcard tasks, and right-aligned tasks on the general kernel), all running concurrently on one page pool."""
