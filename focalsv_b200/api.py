@@ -108,6 +108,9 @@ class Aligner(object):
         if rc != 0:
             raise FsvError(rc, self._lib.fsv_strerror(rc).decode())
         self._h = h
+        for kv in filter(None, os.environ.get("FSV_SET", "").split(",")):      # experiments: FSV_SET=key=value,key=value
+            k, v = kv.split("=")
+            self.set_option(k.strip(), int(v))
 
     def close(self):
         if getattr(self, "_h", None):

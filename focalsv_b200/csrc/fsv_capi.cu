@@ -56,6 +56,7 @@ struct fsv_ctx {
     int64_t page_bytes = 32ll << 20;
     int64_t segment_min_diags = -1;  // tasks with at least this many antidiagonals are cut into segments (0 = off, -1 = auto:
                                      // those whose chain of antidiagonals would outlast 60 % of the batch's throughput time)
+    int segment_warm_pct = 500;      // cold-start lead of a segment, in percent of the band width (+1024 antidiagonals)
     int segment_pool_pct = 45;       // share of the traceback pool the segmented tasks' static pages may take
     int64_t segment_rows = 0;        // target antidiagonals per segment, rounded up to whole traceback pages (0 = auto: 4 x warm-up)
     int lazy_min_pages = 16;    // DPX tasks with at least this many traceback pages take them as they advance (0 = all up front)
@@ -245,6 +246,7 @@ extern "C" int fsv_set_option(fsv_ctx* c, const char* key, int64_t value)
         c->lazy_min_pages = value == 0 ? 0 : (int)std::max<int64_t>(value, 3); return FSV_OK;
     }
     if (!strcmp(key, "segment_min_diags")) { if (value < -1) return FSV_ERR_INVALID; c->segment_min_diags = value; return FSV_OK; }
+    if (!strcmp(key, "segment_warm_pct")) { if (value < 50 || value > 2000) return FSV_ERR_INVALID; c->segment_warm_pct = (int)value; return FSV_OK; }
     if (!strcmp(key, "segment_pool_pct")) { if (value < 1 || value > 90) return FSV_ERR_INVALID; c->segment_pool_pct = (int)value; return FSV_OK; }
     if (!strcmp(key, "segment_rows")) { if (value != 0 && value < 1024) return FSV_ERR_INVALID; c->segment_rows = value; return FSV_OK; }
     if (!strcmp(key, "pool_stall_ms")) { if (value < 100) return FSV_ERR_INVALID; c->pool_stall_ms = (int)value; return FSV_OK; }
@@ -523,7 +525,7 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
             DevTask& d = b->tasks[(size_t)ti];
             const int64_t n_diag = (int64_t)d.qlen + d.tlen - 1;
             const int64_t rpp = d.rows_per_page;
-            const int64_t warm = 5ll * d.w + 1024;                    // generous: a flat cold start is bit-identical well within it (fallback if not)
+            const int64_t warm = (int64_t)c->segment_warm_pct * d.w / 100 + 1024;                    // generous: a flat cold start is bit-identical well within it (fallback if not)
             const int64_t want = c->segment_rows > 0 ? c->segment_rows : std::max<int64_t>(4 * warm, 16384);
             const int64_t seg_rows = std::max<int64_t>(1, (want + rpp - 1) / rpp) * rpp;      // whole pages
             const int n_segs = (int)((n_diag + seg_rows - 1) / seg_rows);

@@ -10,6 +10,7 @@ w = int(sys.argv[3]) if len(sys.argv) > 3 else 3001
 n = int(sys.argv[4]) if len(sys.argv) > 4 else 4
 seg_rows = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 flag = int(sys.argv[6], 0) if len(sys.argv) > 6 else 0
+extra = [a.split("=") for a in sys.argv[7:]]
 rng = np.random.default_rng(11)
 pairs = []
 for i in range(n):
@@ -19,6 +20,7 @@ for i in range(n):
     pairs.append((synth.mutate(rng, q, 0.0008, 0.0002, 0.0002), ref))
 g = synth._pack("seg", preset, pairs, w, PRESETS[preset].zdrop, flag=flag)
 al = api.Aligner(0)
+for k, v in extra: al.set_option(k, int(v))
 out = {}
 for mode, minr in (("whole", 0), ("segmented", 1)):
     al.set_option("segment_min_diags", minr); al.set_option("segment_rows", seg_rows)
