@@ -43,10 +43,18 @@ RESULT_DTYPE = np.dtype([("max", "<i4"), ("zdropped", "<i4"), ("max_q", "<i4"), 
 SIGNATURE_DTYPE = np.dtype([("task", "<i4"), ("svtype", "<i4"), ("pos", "<i8"), ("svlen", "<i4"), ("read_start", "<i4"),
                             ("read_end", "<i4"), ("pad_", "<i4")], align=True)
 PAIR_DTYPE = np.dtype([("a_off", "<i8"), ("b_off", "<i8"), ("a_len", "<i4"), ("b_len", "<i4")], align=True)
+RECORD_DTYPE = np.dtype([("pos", "<i8"), ("ref_end", "<i8"), ("cigar_off", "<i8"), ("n_cigar", "<i4"), ("query_length", "<i4"),
+                         ("score", "<i4"), ("zdropped", "<i4"), ("is_reverse", "<i4"), ("mapq", "<i4")], align=True)
+assert RECORD_DTYPE.itemsize == 48
 assert TASK_DTYPE.itemsize == 40 and RESULT_DTYPE.itemsize == 64 and SIGNATURE_DTYPE.itemsize == 32 and PAIR_DTYPE.itemsize == 24
 
 # fields that must be bit-identical to ksw_extz_t (ksw2.h:23-32)
 EZ_FIELDS = ("max", "zdropped", "max_q", "max_t", "mqe", "mqe_t", "mte", "mte_q", "score", "reach_end", "n_cigar")
+
+
+class PresetC(C.Structure):
+    _fields_ = [("name", C.c_char * 16)] + [(k, C.c_int32) for k in
+                ("a", "b", "q", "e", "q2", "e2", "zdrop", "zdrop_inv", "bw", "bw_long", "sc_ambi", "end_bonus")]
 
 
 class Stats(C.Structure):

@@ -20,7 +20,8 @@ LIB_PATH = os.environ.get("FSV_LIB_PATH") or os.path.join(_HERE, "libfocalsv_cud
 EXPORTS = ("fsv_init", "fsv_destroy", "fsv_strerror", "fsv_last_error", "fsv_abi_version", "fsv_device_count",
            "fsv_get_stats", "fsv_set_option", "fsv_align_batch", "fsv_batch_create", "fsv_batch_run",
            "fsv_batch_fetch", "fsv_batch_destroy", "fsv_ksw_extz2", "fsv_ksw_extd2", "fsv_task_cells",
-           "fsv_lpt_bins", "fsv_measure_int_peak", "fsv_batch_timeline", "fsv_batch_signatures", "fsv_edit_distance_batch")
+           "fsv_lpt_bins", "fsv_measure_int_peak", "fsv_batch_timeline", "fsv_batch_signatures", "fsv_edit_distance_batch",
+           "fsv_preset_lookup", "fsv_realign_regions")
 
 _lib = None
 
@@ -60,6 +61,8 @@ def load_library(path=None):
     lib.fsv_batch_signatures.argtypes = [vp, vp, C.c_int, vp, sz, C.POINTER(sz)]
     lib.fsv_edit_distance_batch.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp]
     lib.fsv_batch_destroy.restype = None
+    lib.fsv_preset_lookup.argtypes = [C.c_char_p, C.POINTER(_abi.PresetC), C.POINTER(Scoring)]
+    lib.fsv_realign_regions.argtypes = [vp, vp, sz, vp, vp, vp, sz, vp, vp, sz, C.c_char_p, C.c_int, C.c_int, vp, vp, sz, C.POINTER(sz)]
     lib.fsv_task_cells.argtypes = [i32, i32, i32]
     lib.fsv_task_cells.restype = i64
     lib.fsv_lpt_bins.argtypes = [vp, sz, C.c_int, vp]
@@ -69,6 +72,16 @@ def load_library(path=None):
     if path is None:
         _lib = lib
     return lib
+
+
+def preset_lookup(name):
+    """(fields dict, Scoring) of a preset as the library knows it (fsv_preset_lookup; host only)."""
+    lib = load_library()
+    p = _abi.PresetC(); sc = Scoring()
+    rc = lib.fsv_preset_lookup(name.encode(), C.byref(p), C.byref(sc))
+    if rc != 0:
+        raise FsvError(rc, "unknown preset %r" % name)
+    return {k: getattr(p, k) for k, _ in _abi.PresetC._fields_[1:]}, sc
 
 
 def task_cells(qlen, tlen, w):
@@ -172,6 +185,29 @@ class Aligner(object):
             raise FsvError(rc, "cigar arena too small: need %d words" % used.value)
         self._check(rc, "fsv_align_batch")
         return out, cig[:used.value]
+
+    def realign_regions(self, ref_codes, region_start, region_end, contig_codes, contig_off, contig_len,
+                        preset="asm5", bw=2000, flag=0, cigar_cap=None):
+        """fsv_realign_regions: contig i against ref_codes[region_start[i]:region_end[i]] with the preset's scoring
+        (the step around DipPAV_variant_call.py:103's minimap2 call).  Returns (records, cigar_arena)."""
+        ref = self._arena(ref_codes); ctg = self._arena(contig_codes)
+        rs = np.ascontiguousarray(region_start, dtype=np.int64); re_ = np.ascontiguousarray(region_end, dtype=np.int64)
+        co = np.ascontiguousarray(contig_off, dtype=np.int64); cl = np.ascontiguousarray(contig_len, dtype=np.int32)
+        n = len(rs)
+        if not (len(re_) == len(co) == len(cl) == n):
+            raise ValueError("realign_regions: one region and one contig per pair")
+        if cigar_cap is None:
+            cigar_cap = int((re_ - rs).sum() + cl.astype(np.int64).sum()) + 2 * n + 16
+        rec = np.zeros(max(n, 1), dtype=_abi.RECORD_DTYPE)
+        cig = np.zeros(max(int(cigar_cap), 1), dtype=np.uint32)
+        used = C.c_size_t(0)
+        rc = self._lib.fsv_realign_regions(self._h, ref.ctypes.data, ref.size, rs.ctypes.data, re_.ctypes.data, ctg.ctypes.data,
+                                           ctg.size, co.ctypes.data, cl.ctypes.data, n, preset.encode(), int(bw), int(flag),
+                                           rec.ctypes.data, cig.ctypes.data, int(cigar_cap), C.byref(used))
+        if rc == _abi.ERR_CIGAR_CAP:
+            raise FsvError(rc, "cigar arena too small: need %d words" % used.value)
+        self._check(rc, "fsv_realign_regions")
+        return rec[:n], cig[:used.value]
 
     def edit_distances(self, seqs_a, seqs_b):
         """Global unit-cost edit distance of seqs_a[i] vs seqs_b[i] (what the reference asks edlib for,

@@ -1025,6 +1025,81 @@ extern "C" int fsv_ksw_extd2(fsv_ctx* c, int qlen, const uint8_t* query, int tle
 }
 
 // ---------------------------------------------------------------------------
+// Level 1: presets and the region hook (host composition over fsv_align_batch)
+static const fsv_preset kPresets[] = {
+    // name        a  b   q   e  q2  e2  zdrop zinv  bw    bw_long sc_ambi end_bonus      (minimap2 2.24 options.c values)
+    {"asm5",       1, 19, 39, 3, 81, 1,  200,  200,  2000, 100000, 1, -1},
+    {"asm10",      1, 9,  16, 2, 41, 1,  200,  200,  2000, 100000, 1, -1},
+    {"map-hifi",   1, 4,  6,  2, 26, 1,  400,  200,  2000, 20000,  1, -1},
+    {"map-pb",     2, 4,  4,  2, 24, 1,  400,  200,  2000, 20000,  1, -1},
+    {"map-ont",    2, 4,  4,  2, 24, 1,  400,  200,  2000, 20000,  1, -1},
+    {"hifiasm",    2, 4,  4,  2, -1, -1, 400,  400,  500,  500,    0, 0},      // Correct.h:1194-1199, Correct.cpp:7670
+};
+
+extern "C" int fsv_preset_lookup(const char* name, fsv_preset* out, fsv_scoring* sc)
+{
+    if (!name) return FSV_ERR_INVALID;
+    for (const fsv_preset& p : kPresets) {
+        if (strcmp(p.name, name)) continue;
+        if (out) *out = p;
+        if (sc) {
+            memset(sc, 0, sizeof *sc);
+            sc->m = 5; sc->q = (int8_t)p.q; sc->e = (int8_t)p.e; sc->q2 = (int8_t)p.q2; sc->e2 = (int8_t)p.e2;
+            for (int i = 0; i < 5; ++i)
+                for (int j = 0; j < 5; ++j)
+                    sc->mat[i * 5 + j] = (int8_t)((i == 4 || j == 4) ? -abs(p.sc_ambi) : i == j ? abs(p.a) : -abs(p.b));
+        }
+        return FSV_OK;
+    }
+    return FSV_ERR_INVALID;
+}
+
+extern "C" int fsv_realign_regions(fsv_ctx* c, const uint8_t* ref_codes, size_t ref_len,
+                                   const int64_t* region_start, const int64_t* region_end,
+                                   const uint8_t* contig_codes, size_t contig_bytes,
+                                   const int64_t* contig_off, const int32_t* contig_len, size_t n,
+                                   const char* preset, int bw, int flag,
+                                   fsv_record* out, uint32_t* cigar, size_t cigar_cap, size_t* cigar_used)
+{
+    if (!c) return FSV_ERR_INVALID;
+    if (cigar_used) *cigar_used = 0;
+    fsv_preset p; fsv_scoring sc;
+    if (fsv_preset_lookup(preset, &p, &sc) != FSV_OK) { c->last_error = "unknown preset"; return FSV_ERR_INVALID; }
+    if (n == 0) return FSV_OK;
+    if (!ref_codes || !region_start || !region_end || !contig_codes || !contig_off || !contig_len || !out || bw < 0)
+        return FSV_ERR_INVALID;
+    const int w = (int)(bw * 1.5 + 1.0);                    // minimap2 runs ksw2 with bw*1.5+1
+    std::vector<fsv_task> tasks(n);
+    for (size_t i = 0; i < n; ++i) {
+        const int64_t s = region_start[i], e = region_end[i];
+        if (s < 0 || e < s || (size_t)e > ref_len || e - s > INT32_MAX || contig_len[i] < 0 || contig_off[i] < 0 ||
+            (size_t)(contig_off[i] + contig_len[i]) > contig_bytes) {
+            c->last_error = "fsv_realign_regions: region or contig " + std::to_string(i) + " outside its arena";
+            return FSV_ERR_INVALID;
+        }
+        fsv_task& t = tasks[i];
+        t.q_off = contig_off[i]; t.t_off = s; t.qlen = contig_len[i]; t.tlen = (int32_t)(e - s);
+        t.w = w; t.zdrop = p.zdrop; t.end_bonus = 0; t.flag = flag & ~FSV_EZ_SCORE_ONLY;
+    }
+    std::vector<fsv_result> res(n);
+    const int rc = fsv_align_batch(c, &sc, contig_codes, contig_bytes, ref_codes, ref_len, tasks.data(), n, res.data(),
+                                   cigar, cigar_cap, cigar_used);
+    if (rc != FSV_OK && rc != FSV_ERR_CIGAR_CAP) return rc;
+    for (size_t i = 0; i < n; ++i) {
+        fsv_record& r = out[i];
+        r.pos = region_start[i]; r.ref_end = region_start[i];
+        r.cigar_off = res[i].cigar_off; r.n_cigar = res[i].n_cigar; r.query_length = contig_len[i];
+        r.score = res[i].score; r.zdropped = res[i].zdropped; r.is_reverse = 0; r.mapq = 60;
+        if (rc == FSV_OK)
+            for (int32_t k = 0; k < r.n_cigar; ++k) {
+                const uint32_t wd = cigar[r.cigar_off + k];
+                if ((wd & 0xf) == 0 || (wd & 0xf) == 2) r.ref_end += wd >> 4;
+            }
+    }
+    return rc;
+}
+
+// ---------------------------------------------------------------------------
 // roofline denominators measured on this device (see fsv_peaks.cuh)
 template <int KIND>
 static int run_peak(fsv_ctx* c, int iters, double* out)

@@ -60,6 +60,22 @@ def realign_regions(aligner, windows, contigs, preset="asm5", bw=2000, flag=0, z
     return records_from_results(windows, contigs, res, arena)
 
 
+def realign_regions_abi(aligner, ref_codes, regions, contigs, preset="asm5", bw=2000, flag=0):
+    """The same step through the library's own Level-1 entry point (fsv_realign_regions): the reference is passed
+    once, regions are (chrom, start, end) into it and are not copied on the host.  Returns AlignedContig records."""
+    q = [encode(s) for _, s in contigs]
+    lens = np.array([len(x) for x in q], dtype=np.int32)
+    offs = np.concatenate([[0], np.cumsum(lens.astype(np.int64))[:-1]]) if len(q) else np.zeros(0, np.int64)
+    rec, arena = aligner.realign_regions(encode(ref_codes), [s for _, s, _ in regions], [e for _, _, e in regions],
+                                         np.concatenate(q) if q else np.zeros(0, np.uint8), offs, lens, preset, bw, flag)
+    out = []
+    for r, (chrom, _, _), (qname, _) in zip(rec, regions, contigs):
+        cig = cigar_tuples(arena[int(r["cigar_off"]):int(r["cigar_off"]) + int(r["n_cigar"])])
+        out.append(AlignedContig(qname, chrom, int(r["pos"]), int(r["ref_end"]), cig, bool(r["is_reverse"]), int(r["mapq"]),
+                                 int(r["query_length"]), int(r["score"]), bool(r["zdropped"])))
+    return out
+
+
 def records_from_results(windows, contigs, res, arena):
     out = []
     for i, ((chrom, start, _), (qname, qseq)) in enumerate(zip(windows, contigs)):

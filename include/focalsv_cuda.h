@@ -131,6 +131,11 @@ int fsv_get_stats(const fsv_ctx* ctx, fsv_stats* out);
  *   "lazy_min_pages"          tasks with at least this many traceback pages take them as they advance (default 16; 0 = off)
  *   "lazy_fill_pct"           such a task starts only while the projected peak of those running stays below this share of the pool (default 65)
  *   "pool_stall_ms"           watchdog of the lazy pool (default 60000)
+ *   "segment_min_diags"       tasks with at least this many antidiagonals are cut into segments that run on separate
+ *                             CTAs (0 = off, -1 = auto, the default: tasks whose chain would outlast 60 % of the batch)
+ *   "segment_rows"            antidiagonals per segment (0 = auto: 4 x the cold-start lead, whole traceback pages)
+ *   "segment_warm_pct"        cold-start lead of a segment in percent of the band width (default 500)
+ *   "segment_pool_pct"        share of the traceback pool the segmented tasks may hold (default 45)
  *   "force_exact"             1 = int8-exact general kernel only
  *   "exact_smem_lanes", "force_excl"   kernel experiments */
 int fsv_set_option(fsv_ctx* ctx, const char* key, int64_t value);
@@ -160,6 +165,46 @@ void fsv_batch_destroy(fsv_batch* batch);
 /* Per-task device timeline of the last run (GPU globaltimer, ns): start_end_ns[2*i] = when task i got its
  * traceback pages and started, [2*i+1] = when its CIGAR was written.  For schedule analysis / tracing. */
 int fsv_batch_timeline(fsv_batch* batch, int64_t* start_end_ns);
+
+/* ---- Level 1: the pipeline hook -------------------------------
+ * What FocalSV does around its `minimap2 -a -x <preset> --cs -r2k ref.fa contigs.fa` call
+ * (focalsv/4_sv_calling/Dippav/DipPAV_variant_call.py:97-137, call_DUP_from_contigs.py:114-126,
+ * align_ins2ref.py:64-71): every haplotype contig of a region against that region's reference window, one record
+ * per (contig, window) pair carrying what the consumers read from pysam today (reference_start, reference_end,
+ * is_reverse, mapping_quality, cigartuples; extract_contig_signature_CCS.py:343-356).  The scoring is the preset's
+ * (minimap2 2.24 values), the band is minimap2's bw*1.5+1 for `-r<bw>`.
+ * The reference is passed once as codes (0..3, other 4); windows are [region_start[i], region_end[i]) into it and are
+ * NOT copied on the host.  contig i = contig_codes[contig_off[i] .. +contig_len[i]).  Each pair is one global
+ * dual-affine task (ksw_extd2_sse with the preset's z-drop); pos = region_start, ref_end = pos + reference bases
+ * the CIGAR consumes.  Errors as fsv_align_batch (FSV_ERR_CIGAR_CAP: records valid, *cigar_used = words needed). */
+typedef struct fsv_preset {
+    char    name[16];         /* "asm5", "asm10", "map-hifi", "map-pb", "map-ont", "hifiasm" (Correct.h:1194-1199) */
+    int32_t a, b, q, e, q2, e2;   /* q2 < 0: single-affine */
+    int32_t zdrop, zdrop_inv;
+    int32_t bw, bw_long;
+    int32_t sc_ambi, end_bonus;
+} fsv_preset;
+/* Host only.  FSV_ERR_INVALID for an unknown name; `sc` (may be NULL) receives the 5x5 matrix minimap2's
+ * ksw_gen_simple_mat builds for the preset. */
+int fsv_preset_lookup(const char* name, fsv_preset* out, fsv_scoring* sc);
+
+typedef struct fsv_record {
+    int64_t pos;              /* reference_start (0-based) */
+    int64_t ref_end;          /* reference_end */
+    int64_t cigar_off;        /* index (uint32 words) into the CIGAR arena */
+    int32_t n_cigar;
+    int32_t query_length;
+    int32_t score;
+    int32_t zdropped;
+    int32_t is_reverse;       /* always 0: strand selection belongs to seeding (row f2) */
+    int32_t mapq;             /* placeholder 60, as a unique full-length contig alignment gets */
+} fsv_record;
+int fsv_realign_regions(fsv_ctx* ctx, const uint8_t* ref_codes, size_t ref_len,
+                        const int64_t* region_start, const int64_t* region_end,
+                        const uint8_t* contig_codes, size_t contig_bytes,
+                        const int64_t* contig_off, const int32_t* contig_len, size_t n,
+                        const char* preset, int bw, int flag,
+                        fsv_record* out, uint32_t* cigar_arena, size_t cigar_cap, size_t* cigar_used);
 
 /* ---- next row: CIGAR -> DEL / INS signatures on the device -------------
  * What the reference does with every aligned contig right after the alignment

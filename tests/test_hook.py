@@ -65,6 +65,40 @@ def test_gpu_region_call_gives_identical_records_and_signatures(oracle, aligner)
     assert hook.signatures(got) == hook.signatures(want)
 
 
+@pytest.mark.gpu
+def test_level1_entry_point_gives_the_same_records(oracle, aligner):
+    """fsv_realign_regions (SURVEY 8b level 1): windows addressed inside ONE reference arena, overlapping allowed."""
+    rng = np.random.default_rng(9)
+    ref = synth.random_seq(rng, 60000)
+    regions, contigs, windows = [], [], []
+    for i, (s, e) in enumerate([(1000, 11000), (8000, 20500), (30000, 39000), (30000, 39000), (59000, 60000)]):
+        q, _ = synth.plant_svs(rng, ref[s:e], 2, max_net=900, max_len=700)
+        q = synth.mutate(rng, q, 0.0006, 0.0002, 0.0002)
+        regions.append(("chr21", s, e)); contigs.append(("contig_hp%d_%d" % (1 + i % 2, i), q)); windows.append(("chr21", s, ref[s:e]))
+    want = _oracle_records(oracle, windows, contigs)
+    got = hook.realign_regions_abi(aligner, ref, regions, contigs, preset="asm5", bw=2000)
+    assert got == want
+    assert hook.realign_regions_abi(aligner, ref, [], [], preset="asm5") == []
+    from focalsv_b200.api import FsvError
+    with pytest.raises(FsvError):
+        hook.realign_regions_abi(aligner, ref, [("chr21", 100, 70000)], contigs[:1])          # window past the reference
+    with pytest.raises(FsvError):
+        hook.realign_regions_abi(aligner, ref, regions[:1], contigs[:1], preset="no-such-preset")
+
+
+def test_library_presets_equal_the_python_table():
+    """fsv_preset_lookup is host-only: the library's preset table and ksw_gen_simple_mat restatement against presets.py."""
+    from focalsv_b200 import api
+    for name, p in PRESETS.items():
+        f, sc = api.preset_lookup(name)
+        assert f == {k: getattr(p, k) for k in f}
+        want = scoring_for(name)
+        assert (sc.m, sc.q, sc.e, sc.q2, sc.e2) == (want.m, want.q, want.e, want.q2, want.e2)
+        assert list(sc.mat)[:25] == list(want.mat)[:25]
+    with pytest.raises(api.FsvError):
+        api.preset_lookup("asm20")
+
+
 def test_signature_rules_match_the_references_own_function():
     """tests/golden/sig_golden.json holds inputs and outputs of the reference's own extract_sig_from_cigar
     (extract_contig_signature_CCS.py:14-127, run by tests/golden/make_sig_golden.py): clips, adjacent I/D,
