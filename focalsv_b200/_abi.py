@@ -1,4 +1,4 @@
-"""ctypes / numpy mirrors of include/focalsv_cuda.h (ABI version 2).
+"""ctypes / numpy mirrors of include/focalsv_cuda.h (ABI version 3).
 
 Kept in one place so that the product binding (focalsv_b200.api), the oracle
 wrapper (oracle/oracle.py) and the tests all see the same layouts.
@@ -7,7 +7,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 NEG_INF = -0x40000000
 
 # ksw2.h:8-14
@@ -62,7 +62,7 @@ class Stats(C.Structure):
                 ("backtrack_launches", C.c_int64), ("other_launches", C.c_int64),
                 ("exact_path_tasks", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("fill_ms", C.c_double), ("backtrack_ms", C.c_double), ("total_ms", C.c_double),
-                ("traceback_bytes", C.c_int64)]
+                ("traceback_bytes", C.c_int64), ("segmented_tasks", C.c_int64), ("segment_fallbacks", C.c_int64)]
 
 
 def simple_mat(a, b, sc_ambi=1, m=5):

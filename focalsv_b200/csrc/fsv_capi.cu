@@ -57,6 +57,8 @@ struct fsv_ctx {
     int64_t segment_min_diags = -1;  // tasks with at least this many antidiagonals are cut into segments (0 = off, -1 = auto:
                                      // those whose chain of antidiagonals would outlast 60 % of the batch's throughput time)
     int segment_warm_pct = 500;      // cold-start lead of a segment, in percent of the band width (+1024 antidiagonals)
+    int segment_extz = 1;            // auto mode: 1 = extension (EXTZ_ONLY) tasks are segmented too, 0 = global tasks only
+    int segment_pool_pct_bound = 25; // the same share when the batch's traceback does not fit the pool
     int segment_pool_pct = 45;       // share of the traceback pool the segmented tasks' static pages may take
     int64_t segment_rows = 0;        // target antidiagonals per segment, rounded up to whole traceback pages (0 = auto: 4 x warm-up)
     int lazy_min_pages = 16;    // DPX tasks with at least this many traceback pages take them as they advance (0 = all up front)
@@ -247,6 +249,8 @@ extern "C" int fsv_set_option(fsv_ctx* c, const char* key, int64_t value)
     }
     if (!strcmp(key, "segment_min_diags")) { if (value < -1) return FSV_ERR_INVALID; c->segment_min_diags = value; return FSV_OK; }
     if (!strcmp(key, "segment_warm_pct")) { if (value < 50 || value > 2000) return FSV_ERR_INVALID; c->segment_warm_pct = (int)value; return FSV_OK; }
+    if (!strcmp(key, "segment_extz")) { c->segment_extz = value != 0; return FSV_OK; }
+    if (!strcmp(key, "segment_pool_pct_bound")) { if (value < 1 || value > 90) return FSV_ERR_INVALID; c->segment_pool_pct_bound = (int)value; return FSV_OK; }
     if (!strcmp(key, "segment_pool_pct")) { if (value < 1 || value > 90) return FSV_ERR_INVALID; c->segment_pool_pct = (int)value; return FSV_OK; }
     if (!strcmp(key, "segment_rows")) { if (value != 0 && value < 1024) return FSV_ERR_INVALID; c->segment_rows = value; return FSV_OK; }
     if (!strcmp(key, "pool_stall_ms")) { if (value < 100) return FSV_ERR_INVALID; c->pool_stall_ms = (int)value; return FSV_OK; }
@@ -502,38 +506,60 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
         // auto: the batch's throughput time if every SM were full (SM-seconds model of the exclusive planning below);
         // a task whose own chain would outlast 60 % of it (or of 20 ms) is worth cutting up
         int64_t min_diags = c->segment_min_diags;
-        if (min_diags < 0) {
-            double W = 0;
-            for (size_t i = 0; i < n; ++i) if (b->is_dpx[i]) {
-                const int nw = b->tasks[i].nw;
-                W += (double)(b->tasks[i].qlen + b->tasks[i].tlen) * (nw <= 2 ? 2.0e-6 : nw == 4 ? 1.8e-6 : 1.55e-6) / (nw == 1 ? 12.0 : nw == 2 ? 6.0 : nw == 4 ? 3.0 : 2.0);
-            }
-            const double t_thr = std::max(W / c->sm_count, 0.020);
-            min_diags = (int64_t)(0.6 * t_thr / 1.55e-6);
+        double W = 0;
+        for (size_t i = 0; i < n; ++i) if (b->is_dpx[i]) {
+            const int nw = b->tasks[i].nw;
+            W += (double)(b->tasks[i].qlen + b->tasks[i].tlen) * (nw <= 2 ? 2.0e-6 : nw == 4 ? 1.8e-6 : 1.55e-6) / (nw == 1 ? 12.0 : nw == 2 ? 6.0 : nw == 4 ? 3.0 : 2.0);
         }
+        const double t_thr = std::max(W / c->sm_count, 0.020);
+        if (min_diags < 0) min_diags = (int64_t)(0.6 * t_thr / 1.55e-6);
         std::vector<int32_t> by_len;
         for (size_t i = 0; i < n; ++i) {
             const DevTask& d = b->tasks[i];
             if (b->is_dpx[i] && d.tb_pages > 0 && !(d.flag & (FSV_EZ_RIGHT | FSV_EZ_SCORE_ONLY | FSV_EZ_APPROX_MAX)) && d.w >= 64 &&
                 (int64_t)d.qlen + d.tlen - 1 >= min_diags &&
-                !(c->segment_min_diags < 0 && (d.flag & FSV_EZ_EXTZ_ONLY)))      // auto: extensions usually end early by z-drop, a segmented task cannot
+                !(c->segment_min_diags < 0 && !c->segment_extz && (d.flag & FSV_EZ_EXTZ_ONLY)))      // an extension may end early by z-drop and its later segments are then wasted work: only tasks that decide the batch time anyway get here
                 by_len.push_back((int32_t)i);
         }
         std::stable_sort(by_len.begin(), by_len.end(), [&](int32_t a, int32_t x) { return b->tasks[a].qlen + b->tasks[a].tlen > b->tasks[x].qlen + b->tasks[x].tlen; });
         std::vector<std::vector<int32_t>> per_nw(9);
-        for (int32_t ti : by_len) {
-            DevTask& d = b->tasks[(size_t)ti];
-            const int64_t n_diag = (int64_t)d.qlen + d.tlen - 1;
-            const int64_t rpp = d.rows_per_page;
-            const int64_t warm = (int64_t)c->segment_warm_pct * d.w / 100 + 1024;                    // generous: a flat cold start is bit-identical well within it (fallback if not)
-            const int64_t want = c->segment_rows > 0 ? c->segment_rows : std::max<int64_t>(4 * warm, 16384);
-            const int64_t seg_rows = std::max<int64_t>(1, (want + rpp - 1) / rpp) * rpp;      // whole pages
-            const int n_segs = (int)((n_diag + seg_rows - 1) / seg_rows);
-            if (n_segs < 2 || seg_rows < 2 * warm) continue;
+        struct SegPlan { int32_t ti; int64_t seg_rows, warm; int n_segs; };
+        std::vector<SegPlan> plan;
+        {
             // static pages: a share of the pool; smaller when the batch's traceback does not fit the pool anyway (then the
             // pool, not the longest chain, is what the batch waits for: measured on cfg2, 25 % is neutral, 45 % costs 14 %)
-            const int pct = b->pages_total > b->cap_pages ? std::min(c->segment_pool_pct, 25) : c->segment_pool_pct;
-            if ((b->seg_static_pages + d.tb_pages) * 100 > b->cap_pages * pct) continue;
+            // ... unless the longest chain alone is more than twice the batch's throughput time: then the chain is what the
+            // batch waits for whatever the pool does (cfg4 at 1/4 scale: 3.5 s whole, 1.29 s with 25 %, 0.87 s with 45 %)
+            const bool chain_bound = !by_len.empty() && (double)(b->tasks[(size_t)by_len[0]].qlen + b->tasks[(size_t)by_len[0]].tlen) * 1.3e-6 > 2.0 * t_thr;
+            const int pct = b->pages_total > b->cap_pages && !chain_bound ? std::min(c->segment_pool_pct, c->segment_pool_pct_bound) : c->segment_pool_pct;
+            int64_t pages = 0, longest_in = 0, longest_out = 0;
+            for (int32_t ti : by_len) {
+                const DevTask& d = b->tasks[(size_t)ti];
+                const int64_t n_diag = (int64_t)d.qlen + d.tlen - 1;
+                const int64_t rpp = d.rows_per_page;
+                const int64_t warm = (int64_t)c->segment_warm_pct * d.w / 100 + 1024;                    // generous: a flat cold start is bit-identical well within it (fallback if not)
+                const int64_t want = c->segment_rows > 0 ? c->segment_rows : std::max<int64_t>(4 * warm, 16384);
+                const int64_t seg_rows = std::max<int64_t>(1, (want + rpp - 1) / rpp) * rpp;      // whole pages
+                const int n_segs = (int)((n_diag + seg_rows - 1) / seg_rows);
+                if (n_segs < 2 || seg_rows < 2 * warm) continue;
+                if ((pages + d.tb_pages) * 100 > b->cap_pages * pct) { longest_out = std::max(longest_out, n_diag); continue; }
+                pages += d.tb_pages; longest_in = std::max(longest_in, n_diag);
+                plan.push_back({ti, seg_rows, warm, n_segs});
+            }
+            // auto: the batch still waits for the longest task that stays whole; if the pool share ran out before the chains
+            // got markedly shorter, the segments would only add their warm-up work (cfg4: 3.5 -> 3.9 s) - leave every task whole
+            const size_t planned = plan.size();
+            if (c->segment_min_diags < 0 && longest_out * 10 > longest_in * 7) plan.clear();
+            if (getenv("FSV_TRACE"))
+                fprintf(stderr, "[fsv] segment plan: min_diags %lld, eligible %zu, within the pool share (%d %%) %zu (%lld pages of %lld), longest in %lld / left whole %lld -> %zu tasks segmented\n",
+                        (long long)min_diags, by_len.size(), pct, planned, (long long)pages, (long long)b->cap_pages, (long long)longest_in, (long long)longest_out, plan.size());
+        }
+        for (const SegPlan& sp : plan) {
+            const int32_t ti = sp.ti;
+            DevTask& d = b->tasks[(size_t)ti];
+            const int64_t n_diag = (int64_t)d.qlen + d.tlen - 1;
+            const int64_t warm = sp.warm, seg_rows = sp.seg_rows;
+            const int n_segs = sp.n_segs;
             SegTask st{};
             st.rec_off = b->seg_rec_total; st.snap_off = b->seg_snap_words; st.table_off = (int32_t)b->seg_pages.size();
             st.n_segs = n_segs; st.first_seg = (int32_t)b->segs.size();
@@ -761,7 +787,9 @@ extern "C" int fsv_batch_run(fsv_batch* b)
     // every kernel variant runs concurrently on its own stream; they share the page pool, so the long
     // tasks of one class overlap the short tasks of all the others
     int32_t slot_base = 0;
-    // segments of the long tasks first: they are what the batch waits for
+    // order: exclusive launches (their CTAs need EMPTY SMs: behind the segments they would wait for a whole SM to
+    // drain), then the segments of the long tasks (what the batch waits for), then everything else
+    auto launch_segments = [&]() -> int {
     for (size_t i = 0; i < b->seg_launches.size(); ++i) {
         const auto& L = b->seg_launches[i];
         const size_t qi = b->launches.size() + i;
@@ -777,7 +805,9 @@ extern "C" int fsv_batch_run(fsv_batch* b)
         CK(c, cudaEventRecord(done[qi], ks));
         CK(c, cudaStreamWaitEvent(c->stream, done[qi], 0));
     }
-    for (size_t i = 0; i < b->launches.size(); ++i) {
+    return FSV_OK;
+    };
+    auto launch_one = [&](size_t i) -> int {
         const Launch& L = b->launches[i];
         cudaStream_t ks = c->kstream[i] ? c->kstream[i] : c->stream;
         CK(c, cudaStreamWaitEvent(ks, e0, 0));
@@ -799,7 +829,13 @@ extern "C" int fsv_batch_run(fsv_batch* b)
         CK(c, cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
         CK(c, cudaEventRecord(done[i], ks));
         CK(c, cudaStreamWaitEvent(c->stream, done[i], 0));
-    }
+        return FSV_OK;
+    };
+    for (size_t i = 0; i < b->launches.size(); ++i)
+        if (b->launches[i].kind == 1 && b->launches[i].excl && (rc = launch_one(i)) != FSV_OK) return rc;
+    if ((rc = launch_segments()) != FSV_OK) return rc;
+    for (size_t i = 0; i < b->launches.size(); ++i)
+        if (!(b->launches[i].kind == 1 && b->launches[i].excl) && (rc = launch_one(i)) != FSV_OK) return rc;
     CK(c, cudaEventRecord(e1, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     tr.lap("run: kernels");
@@ -809,6 +845,13 @@ extern "C" int fsv_batch_run(fsv_batch* b)
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     c->stats.total_ms = ms; c->stats.fill_ms = ms; c->stats.backtrack_ms = 0;   // the CIGAR walk runs inside the fill kernels
     c->stats.traceback_bytes = b->tb_bytes_total;
+    c->stats.segmented_tasks = (int64_t)b->seg_tasks.size();
+    c->stats.segment_fallbacks = 0;
+    if (!b->seg_tasks.empty()) {
+        std::vector<int32_t> sd(b->seg_tasks.size());
+        CK(c, cudaMemcpy(sd.data(), b->d_seg_done, sd.size() * 4, cudaMemcpyDeviceToHost));
+        for (int32_t v : sd) c->stats.segment_fallbacks += v >= (1 << 20);
+    }
     c->stats.tasks += (int64_t)b->n;
     int64_t ne = 0;
     for (size_t i = 0; i < b->n; ++i) if (!b->is_dpx[i]) ++ne;

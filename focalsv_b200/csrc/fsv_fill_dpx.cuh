@@ -727,9 +727,55 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
             __syncthreads();
             if (!lds32(sb + OFF_SEG)) continue;
             __threadfence();
-            // (1) every boundary: the state segment b+1 reached from its cold start == the state segment b reached
+            // (1) warp 0 replays the ksw_extz_t bookkeeping (:262-269) over the records, 32 at a time, and finds the segment
+            // the alignment ends in (z-drop, band exhausted, or the last one).  The records of segment k are the true ones if
+            // the boundaries below k hold, which (2) checks afterwards: segments BEHIND the end (an extension that z-dropped
+            // early ran on unrelated sequence there, where a cold start need not converge) are never looked at.
+            EzState e2; e2.reset();
+            int64_t cells2 = 0;
+            if (warp == 0) {
+                int32_t delta = 0;
+                bool stop = false;
+                int stop_seg = G.count - 1;
+                for (int sgi = 0; sgi < G.count && !stop; ++sgi) {
+                    const DevSeg Gs = C.segs[ST.first_seg + sgi];
+                    const int foot = ((volatile int32_t*)C.seg_foot)[ST.first_seg + sgi];
+                    const int end = foot >= 0 ? foot : Gs.r_end;
+                    for (int d0 = Gs.r_begin; d0 < end && !stop; d0 += 32) {
+                        int4 rec = make_int4(0, 0, 0, 0);
+                        if (d0 + lane < end) rec = __ldcg(C.seg_rec + ST.rec_off + d0 + lane);
+                        const int nrec = min(32, end - d0);
+                        for (int k = 0; k < nrec; ++k) {
+                            const int d = d0 + k;
+                            const int32_t M = __shfl_sync(FULL, rec.x, k) + delta;
+                            const int max_t = __shfl_sync(FULL, rec.y, k);
+                            int32_t hen0 = __shfl_sync(FULL, rec.z, k), hst0 = __shfl_sync(FULL, rec.w, k);
+                            int st0d, en0d;
+                            band_limits(d, qlen, tlen, w, st0d, en0d);
+                            cells2 += en0d - st0d + 1;
+                            if (hen0 != FSV_NEG_INF) hen0 += delta;
+                            if (hst0 != FSV_NEG_INF) hst0 += delta;
+                            if (en0d == tlen - 1 && hen0 > e2.mte) { e2.mte = hen0; e2.mte_q = d - round_en(en0d); }
+                            if (d - st0d == qlen - 1 && hst0 > e2.mqe) { e2.mqe = hst0; e2.mqe_t = st0d; }
+                            if (e2.apply_zdrop(M, d, max_t, T.zdrop, sc.e_drop)) { stop = true; break; }
+                            if (d == n_diag - 1 && en0d == tlen - 1) e2.score = hen0;
+                        }
+                    }
+                    if (!stop && foot >= 0) { e2.zdropped = 1; stop = true; }                     // band exhausted (:111-114)
+                    if (stop) stop_seg = sgi;
+                    if (!stop && sgi + 1 < G.count) {
+                        const uint32_t* A = C.seg_snap + ST.snap_off + (int64_t)(2 * sgi) * SEG_SNAP_WORDS;
+                        delta += (int32_t)__ldcg(A) - (int32_t)__ldcg(A + SEG_SNAP_WORDS);
+                    }
+                }
+                if (lane == 0) sts32(sb + OFF_SEG, (uint32_t)stop_seg);
+            }
+            __syncthreads();
+            const int n_bound = (int)lds32(sb + OFF_SEG);      // boundaries 0 .. n_bound-1 carry the result
+            __syncthreads();
+            // (2) those boundaries: the state segment b+1 reached from its cold start == the state segment b reached
             bool bad = false;
-            for (int b = 0; b + 1 < G.count; ++b) {
+            for (int b = 0; b < n_bound; ++b) {
                 if (((volatile int32_t*)C.seg_foot)[ST.first_seg + b] >= 0) break;       // the alignment ends inside segment b
                 const int rb = C.segs[ST.first_seg + b].r_end - 1;
                 int st0b, en0b;
@@ -781,45 +827,12 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                     }
                 }
             }
-            if (__syncthreads_or(bad)) { seg_redo = ST.first_seg; continue; }      // re-run the task whole (this CTA, static pages)
-            // (2) warp 0 replays the ksw_extz_t bookkeeping (:262-269) over the records, 32 at a time
-            if (warp == 0) {
-                EzState e2; e2.reset();
-                int64_t cells2 = 0;
-                int32_t delta = 0;
-                bool stop = false;
-                for (int sgi = 0; sgi < G.count && !stop; ++sgi) {
-                    const DevSeg Gs = C.segs[ST.first_seg + sgi];
-                    const int foot = ((volatile int32_t*)C.seg_foot)[ST.first_seg + sgi];
-                    const int end = foot >= 0 ? foot : Gs.r_end;
-                    for (int d0 = Gs.r_begin; d0 < end && !stop; d0 += 32) {
-                        int4 rec = make_int4(0, 0, 0, 0);
-                        if (d0 + lane < end) rec = __ldcg(C.seg_rec + ST.rec_off + d0 + lane);
-                        const int nrec = min(32, end - d0);
-                        for (int k = 0; k < nrec; ++k) {
-                            const int d = d0 + k;
-                            const int32_t M = __shfl_sync(FULL, rec.x, k) + delta;
-                            const int max_t = __shfl_sync(FULL, rec.y, k);
-                            int32_t hen0 = __shfl_sync(FULL, rec.z, k), hst0 = __shfl_sync(FULL, rec.w, k);
-                            int st0d, en0d;
-                            band_limits(d, qlen, tlen, w, st0d, en0d);
-                            cells2 += en0d - st0d + 1;
-                            if (hen0 != FSV_NEG_INF) hen0 += delta;
-                            if (hst0 != FSV_NEG_INF) hst0 += delta;
-                            if (en0d == tlen - 1 && hen0 > e2.mte) { e2.mte = hen0; e2.mte_q = d - round_en(en0d); }
-                            if (d - st0d == qlen - 1 && hst0 > e2.mqe) { e2.mqe = hst0; e2.mqe_t = st0d; }
-                            if (e2.apply_zdrop(M, d, max_t, T.zdrop, sc.e_drop)) { stop = true; break; }
-                            if (d == n_diag - 1 && en0d == tlen - 1) e2.score = hen0;
-                        }
-                    }
-                    if (!stop && foot >= 0) { e2.zdropped = 1; stop = true; }                     // band exhausted (:111-114)
-                    if (!stop && sgi + 1 < G.count) {
-                        const uint32_t* A = C.seg_snap + ST.snap_off + (int64_t)(2 * sgi) * SEG_SNAP_WORDS;
-                        delta += (int32_t)__ldcg(A) - (int32_t)__ldcg(A + SEG_SNAP_WORDS);
-                    }
-                }
-                finish_task(C, T, table, e2, cells2, TB);
+            if (__syncthreads_or(bad)) {         // re-run the task whole (this CTA, static pages)
+                if (tid == 0) atomicAdd(&C.seg_done[T.seg_id], 1 << 20);      // counted by the host (fsv_stats.segment_fallbacks)
+                seg_redo = ST.first_seg;
+                continue;
             }
+            if (warp == 0) finish_task(C, T, table, e2, cells2, TB);
             __syncthreads();
             if (tid == 0) {
                 pool_free(C.pool, T.tb_pages, table);      // the task's static pages join the dynamic pool

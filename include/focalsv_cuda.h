@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define FSV_ABI_VERSION 2
+#define FSV_ABI_VERSION 3
 
 /* ksw2.h:6 */
 #define FSV_NEG_INF (-0x40000000)
@@ -110,6 +110,8 @@ typedef struct fsv_stats {
     double  backtrack_ms;     /* CUDA-event time of backtrack kernels (last run) */
     double  total_ms;         /* CUDA-event time of the last fsv_batch_run */
     int64_t traceback_bytes;  /* traceback bytes written by the last run */
+    int64_t segmented_tasks;  /* last run: long tasks cut into segments that ran on separate SMs */
+    int64_t segment_fallbacks;/* last run: of those, tasks whose boundary check failed and that were run again whole */
 } fsv_stats;
 
 typedef struct fsv_ctx fsv_ctx;
@@ -136,6 +138,7 @@ int fsv_get_stats(const fsv_ctx* ctx, fsv_stats* out);
  *   "segment_rows"            antidiagonals per segment (0 = auto: 4 x the cold-start lead, whole traceback pages)
  *   "segment_warm_pct"        cold-start lead of a segment in percent of the band width (default 500)
  *   "segment_pool_pct"        share of the traceback pool the segmented tasks may hold (default 45)
+ *   "segment_extz"            auto mode: 1 = extension (EXTZ_ONLY) tasks are segmented too (default), 0 = global tasks only
  *   "force_exact"             1 = int8-exact general kernel only
  *   "exact_smem_lanes", "force_excl"   kernel experiments */
 int fsv_set_option(fsv_ctx* ctx, const char* key, int64_t value);

@@ -7,6 +7,7 @@ from focalsv_b200 import api, _abi, synth
 from util import same_result
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 0.1
 ncheck = int(sys.argv[2]) if len(sys.argv) > 2 else 6
+only = sys.argv[3].split(",") if len(sys.argv) > 3 else None      # e.g. cfg3,cfg4
 al = api.Aligner(0)
 cfgs = {
     "cfg1": lambda: synth.config1(n_reads=max(8, int(400 * scale))),
@@ -15,6 +16,8 @@ cfgs = {
     "cfg4": lambda: synth.config4(n_dup=max(4, int(213 * scale)), n_pair=max(4, int(270 * scale)), max_region=1500000),
 }
 for name, mk in cfgs.items():
+    if only and name not in only:
+        continue
     t0 = time.time(); groups = mk(); tg = time.time() - t0
     for g in groups:
         b = al.batch(g.scoring, g.qarena, g.tarena, g.tasks); b.run(); b.run(); s = al.stats(); res, cig = b.fetch(); b.close()

@@ -350,6 +350,12 @@ def test_segmented_long_tasks(oracle, preset, w):
     pairs.append((q, ref)); flags.append(0)
     ref = synth.random_seq(rng, L)
     pairs.append((synth.mutate(rng, ref, 0.002, 0.001, 0.001), ref)); flags.append(_abi.EZ_EXTZ_ONLY | _abi.EZ_REV_CIGAR)
+    for fl in (_abi.EZ_EXTZ_ONLY, 0):                                                         # diverges at 1/4: the segments behind the
+        ref = synth.random_seq(rng, L)                                                        # z-drop run on unrelated sequence, where a cold
+        q = synth.mutate(rng, ref, 0.001, 0.0003, 0.0003)                                     # start need not converge; they must not be
+        q = np.concatenate([q[: L // 4], synth.random_seq(rng, 3 * L // 4)])                  # looked at (no fallback)
+        pairs.append((q, ref)); flags.append(fl)
+    n_long = len(pairs)
     for Ls in (300, 2500, 9000):                                                              # short company
         ref = synth.random_seq(rng, Ls)
         pairs.append((synth.mutate(rng, ref, 0.01, 0.004, 0.004), ref)); flags.append(0)
@@ -359,7 +365,10 @@ def test_segmented_long_tasks(oracle, preset, w):
         al.set_option("segment_min_diags", 50000)          # force: every long task is segmented, extensions included
         bad, ores, gres = compare_group(oracle, al, g, threads=16)
         assert not bad, bad
-        assert int(gres["zdropped"][2]) == 1
+        assert int(gres["zdropped"][2]) == 1 and int(gres["zdropped"][4]) == 1 and int(gres["zdropped"][5]) == 1
+        st = al.stats()
+        assert st["segmented_tasks"] == n_long
+        assert st["segment_fallbacks"] <= 1, st              # at most the identical pair
         launches_seg = al.stats()["fill_launches"]
         al.set_option("segment_min_diags", 0)               # and the same batch unsegmented
         bad, _, _ = compare_group(oracle, al, g, threads=16)
