@@ -546,10 +546,7 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
                 pages += d.tb_pages; longest_in = std::max(longest_in, n_diag);
                 plan.push_back({ti, seg_rows, warm, n_segs});
             }
-            // auto: the batch still waits for the longest task that stays whole; if the pool share ran out before the chains
-            // got markedly shorter, the segments would only add their warm-up work (cfg4: 3.5 -> 3.9 s) - leave every task whole
             const size_t planned = plan.size();
-            if (c->segment_min_diags < 0 && longest_out * 10 > longest_in * 7) plan.clear();
             if (getenv("FSV_TRACE"))
                 fprintf(stderr, "[fsv] segment plan: min_diags %lld, eligible %zu, within the pool share (%d %%) %zu (%lld pages of %lld), longest in %lld / left whole %lld -> %zu tasks segmented\n",
                         (long long)min_diags, by_len.size(), pct, planned, (long long)pages, (long long)b->cap_pages, (long long)longest_in, (long long)longest_out, plan.size());

@@ -27,7 +27,7 @@ for mode, minr in (("whole", 0), ("segmented", 1)):
     b = al.batch(g.scoring, g.qarena, g.tarena, g.tasks); b.run(); b.run()
     ms = al.stats()["total_ms"]; res, cig = b.fetch(); b.close()
     out[mode] = (res, cig)
-    print("%-9s %8.1f ms  %.1f GCUPS  zdropped %d  launches %d" % (mode, ms, int(res["cells"].sum()) / ms / 1e6, int(res["zdropped"].sum()), al.stats()["fill_launches"]), flush=True)
+    print("%-9s %8.1f ms  %.1f GCUPS  zdropped %d  launches %d" % (mode, ms, int(res["cells"].sum()) / ms / 1e6, int(res["zdropped"].sum()), al.stats()["fill_launches"]), "segmented %d fallbacks %d" % (al.stats()["segmented_tasks"], al.stats()["segment_fallbacks"]), flush=True)
 ra, ca = out["whole"]; rb, cb = out["segmented"]
 bad = 0
 for i in range(n):

@@ -34,6 +34,41 @@ def test_struct_layouts_match_header():
     assert _abi.RESULT_DTYPE.fields["cigar_off"][1] == 48 and _abi.RESULT_DTYPE.fields["cells"][1] == 56
 
 
+def test_header_compiles_as_c_and_layouts_equal_the_python_mirrors(tmp_path):
+    """include/focalsv_cuda.h is plain C: gcc compiles a probe against it and the sizes / offsets it prints are the ones
+    the ctypes structures and numpy dtypes of focalsv_b200/_abi.py use."""
+    import shutil, subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    structs = {"fsv_task": _abi.TASK_DTYPE, "fsv_result": _abi.RESULT_DTYPE, "fsv_signature": _abi.SIGNATURE_DTYPE,
+               "fsv_pair": _abi.PAIR_DTYPE, "fsv_record": _abi.RECORD_DTYPE}
+    cstructs = {"fsv_scoring": _abi.Scoring, "fsv_stats": _abi.Stats, "fsv_preset": _abi.PresetC}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "focalsv_cuda.h"', 'int main(void) {']
+    for name, dt in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (name, name))
+        for f in dt.names:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (name, f, name, f))
+    for name, st in cstructs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (name, name))
+        for f, _ in st._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (name, f, name, f))
+    lines += ['printf("abi %d\\n", FSV_ABI_VERSION);', 'return 0; }']
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", inc, str(src), "-o", str(tmp_path / "probe")])
+    got = dict(l.split() for l in subprocess.check_output([str(tmp_path / "probe")]).decode().splitlines())
+    for name, dt in structs.items():
+        assert int(got[name]) == dt.itemsize, name
+        for f in dt.names:
+            assert int(got["%s.%s" % (name, f)]) == dt.fields[f][1], (name, f)
+    for name, st in cstructs.items():
+        assert int(got[name]) == C.sizeof(st), name
+        for f, _ in st._fields_:
+            assert int(got["%s.%s" % (name, f)]) == getattr(st, f).offset, (name, f)
+    assert int(got["abi"]) == _abi.ABI_VERSION
+
+
 def test_no_cpu_fallback_without_device():
     lib = api.load_library()
     if lib.fsv_device_count() > 0:
