@@ -56,7 +56,7 @@ struct fsv_ctx {
     int64_t page_bytes = 32ll << 20;
     int64_t segment_min_diags = -1;  // tasks with at least this many antidiagonals are cut into segments (0 = off, -1 = auto:
                                      // those whose chain of antidiagonals would outlast 60 % of the batch's throughput time)
-    int segment_warm_pct = 500;      // cold-start lead of a segment, in percent of the band width (+1024 antidiagonals)
+    int segment_warm_pct = 400;      // cold-start lead of a segment, in percent of the band width (+1024 antidiagonals)
     int segment_extz = 1;            // auto mode: 1 = extension (EXTZ_ONLY) tasks are segmented too, 0 = global tasks only
     int segment_pool_pct_bound = 25; // the same share when the batch's traceback does not fit the pool
     int segment_pool_pct = 45;       // share of the traceback pool the segmented tasks' static pages may take

@@ -459,7 +459,12 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
             };
             if (r < stop_r) {
                 band_limits(r, qlen, tlen, w, st0, en0);
-                if (st0 > en0) stop_r = r; else valid = true;
+                if (st0 > en0) {
+                    stop_r = r;
+                    // a segment whose cold start already lies behind the end of the band (|qlen - tlen| > w) has nothing to compute;
+                    // section (A) would never meet d == stop_r - 1 and run on past the task's records
+                    if (SEG && segmode && r == rz) break;
+                } else valid = true;
             }
             act_p = false;
             if (valid) {
@@ -742,24 +747,58 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                     const int foot = ((volatile int32_t*)C.seg_foot)[ST.first_seg + sgi];
                     const int end = foot >= 0 ? foot : Gs.r_end;
                     for (int d0 = Gs.r_begin; d0 < end && !stop; d0 += 32) {
+                        // one record per lane; ksw_apply_zdrop's running maximum (ksw2.h:160-176: a later record wins only if
+                        // strictly greater) is an inclusive warp scan with the state so far as the earliest element, every lane
+                        // tests its own record against the maximum BEFORE it, and the first lane that drops ends the replay
+                        const bool valid = d0 + lane < end;
                         int4 rec = make_int4(0, 0, 0, 0);
-                        if (d0 + lane < end) rec = __ldcg(C.seg_rec + ST.rec_off + d0 + lane);
-                        const int nrec = min(32, end - d0);
-                        for (int k = 0; k < nrec; ++k) {
-                            const int d = d0 + k;
-                            const int32_t M = __shfl_sync(FULL, rec.x, k) + delta;
-                            const int max_t = __shfl_sync(FULL, rec.y, k);
-                            int32_t hen0 = __shfl_sync(FULL, rec.z, k), hst0 = __shfl_sync(FULL, rec.w, k);
-                            int st0d, en0d;
-                            band_limits(d, qlen, tlen, w, st0d, en0d);
-                            cells2 += en0d - st0d + 1;
-                            if (hen0 != FSV_NEG_INF) hen0 += delta;
-                            if (hst0 != FSV_NEG_INF) hst0 += delta;
-                            if (en0d == tlen - 1 && hen0 > e2.mte) { e2.mte = hen0; e2.mte_q = d - round_en(en0d); }
-                            if (d - st0d == qlen - 1 && hst0 > e2.mqe) { e2.mqe = hst0; e2.mqe_t = st0d; }
-                            if (e2.apply_zdrop(M, d, max_t, T.zdrop, sc.e_drop)) { stop = true; break; }
-                            if (d == n_diag - 1 && en0d == tlen - 1) e2.score = hen0;
+                        if (valid) rec = __ldcg(C.seg_rec + ST.rec_off + d0 + lane);
+                        const int d = d0 + lane;
+                        int st0d, en0d;
+                        band_limits(valid ? d : 0, qlen, tlen, w, st0d, en0d);
+                        const int32_t M = valid ? rec.x + delta : (int32_t)0x80000000;
+                        const int mt = rec.y, mq = d - rec.y;
+                        int32_t pm = M; int pt = mt, pq = mq;
+#pragma unroll
+                        for (int off = 1; off < 32; off <<= 1) {
+                            const int32_t om = __shfl_up_sync(FULL, pm, off);
+                            const int ot = __shfl_up_sync(FULL, pt, off), oq = __shfl_up_sync(FULL, pq, off);
+                            if (lane >= off && !(pm > om)) { pm = om; pt = ot; pq = oq; }
                         }
+                        int32_t bm = __shfl_up_sync(FULL, pm, 1); int bt = __shfl_up_sync(FULL, pt, 1), bq = __shfl_up_sync(FULL, pq, 1);
+                        if (lane == 0 || !(bm > e2.max)) { bm = e2.max; bt = e2.max_t; bq = e2.max_q; }      // the maximum before this record
+                        bool drops = false;
+                        if (valid && !(M > bm) && mt >= bt && mq >= bq) {
+                            const int tl = mt - bt, ql = mq - bq, l = tl > ql ? tl - ql : ql - tl;
+                            drops = T.zdrop >= 0 && bm - M > T.zdrop + l * sc.e_drop;
+                        }
+                        const uint32_t dmask = __ballot_sync(FULL, drops);
+                        const int first = dmask ? __ffs((int)dmask) - 1 : -1;
+                        const int nproc = first >= 0 ? first + 1 : min(32, end - d0);      // records that count, the dropping one included
+                        const bool inc = lane < nproc;
+                        {   // maximum after the last counted record
+                            const int32_t lm = __shfl_sync(FULL, pm, nproc - 1);
+                            const int lt = __shfl_sync(FULL, pt, nproc - 1), lq = __shfl_sync(FULL, pq, nproc - 1);
+                            if (lm > e2.max) { e2.max = (int32_t)((uint32_t)lm & 0x7fffffffu); e2.max_t = lt; e2.max_q = lq; }
+                        }
+                        cells2 += (int64_t)__reduce_add_sync(FULL, inc ? (uint32_t)(en0d - st0d + 1) : 0u);
+                        {   // mte / mqe (:262-267): strictly greater, so the FIRST record holding the chunk's maximum
+                            const int32_t he = (inc && en0d == tlen - 1 && rec.z != FSV_NEG_INF) ? rec.z + delta : FSV_NEG_INF;
+                            const int32_t mx = __reduce_max_sync(FULL, he);
+                            if (mx > e2.mte) {
+                                const int L = __ffs((int)__ballot_sync(FULL, he == mx)) - 1;
+                                e2.mte = mx; e2.mte_q = __shfl_sync(FULL, d - round_en(en0d), L);
+                            }
+                            const int32_t hs = (inc && d - st0d == qlen - 1 && rec.w != FSV_NEG_INF) ? rec.w + delta : FSV_NEG_INF;
+                            const int32_t mx2 = __reduce_max_sync(FULL, hs);
+                            if (mx2 > e2.mqe) {
+                                const int L = __ffs((int)__ballot_sync(FULL, hs == mx2)) - 1;
+                                e2.mqe = mx2; e2.mqe_t = __shfl_sync(FULL, st0d, L);
+                            }
+                            const uint32_t last = __ballot_sync(FULL, inc && lane != first && d == n_diag - 1 && en0d == tlen - 1);
+                            if (last) e2.score = __shfl_sync(FULL, rec.z != FSV_NEG_INF ? rec.z + delta : FSV_NEG_INF, __ffs((int)last) - 1);
+                        }
+                        if (first >= 0) { e2.zdropped = 1; stop = true; }
                     }
                     if (!stop && foot >= 0) { e2.zdropped = 1; stop = true; }                     // band exhausted (:111-114)
                     if (stop) stop_seg = sgi;

@@ -11,9 +11,9 @@ only = sys.argv[3].split(",") if len(sys.argv) > 3 else None      # e.g. cfg3,cf
 al = api.Aligner(0)
 cfgs = {
     "cfg1": lambda: synth.config1(n_reads=max(8, int(400 * scale))),
-    "cfg2": lambda: synth.config2(n_regions=max(8, int(5000 * scale)), max_region=400000),
-    "cfg3": lambda: synth.config3(n_regions=max(8, int(2000 * scale)), max_region=200000),
-    "cfg4": lambda: synth.config4(n_dup=max(4, int(213 * scale)), n_pair=max(4, int(270 * scale)), max_region=1500000),
+    "cfg2": lambda: synth.config2(n_regions=max(8, int(5000 * scale)), max_region=None if scale >= 1 else 400000),
+    "cfg3": lambda: synth.config3(n_regions=max(8, int(2000 * scale)), max_region=None if scale >= 1 else 200000),
+    "cfg4": lambda: synth.config4(n_dup=max(4, int(213 * scale)), n_pair=max(4, int(270 * scale)), max_region=None if scale >= 1 else 1500000),
 }
 for name, mk in cfgs.items():
     if only and name not in only:
@@ -30,4 +30,5 @@ for name, mk in cfgs.items():
             bad += 0 if (same_result(ores[k], oc, res[i], api.task_cigar(res[i], cig)) and int(ores[k]["cells"]) == int(res[i]["cells"])) else 1
         print("%-26s tasks %5d regions %5d cells %.3e  %.1f ms  %.1f GCUPS  %.0f regions/s  zdropped %d  general-kernel tasks %d  parity %d/%d ok" % (
             g.name, len(g.tasks), regions, cells, s["total_ms"], cells / s["total_ms"] / 1e6, regions / s["total_ms"] * 1e3,
-            int(res["zdropped"].sum()), int((al.stats()["exact_path_tasks"])), len(small) - bad, len(small)), flush=True)
+            int(res["zdropped"].sum()), int((al.stats()["exact_path_tasks"])), len(small) - bad, len(small)),
+            " segmented %d (fallbacks %d)" % (s["segmented_tasks"], s["segment_fallbacks"]), flush=True)

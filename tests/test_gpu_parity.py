@@ -355,6 +355,9 @@ def test_segmented_long_tasks(oracle, preset, w):
         q = synth.mutate(rng, ref, 0.001, 0.0003, 0.0003)                                     # start need not converge; they must not be
         q = np.concatenate([q[: L // 4], synth.random_seq(rng, 3 * L // 4)])                  # looked at (no fallback)
         pairs.append((q, ref)); flags.append(fl)
+    ref = synth.random_seq(rng, L)                                                            # |qlen - tlen| > w: the band runs out before the
+    q = np.concatenate([synth.mutate(rng, ref, 0.001, 0.0003, 0.0003), synth.random_seq(rng, 60000 if w == 500 else 140000)])
+    pairs.append((q, ref)); flags.append(0)                                                   # end and whole segments start behind it
     n_long = len(pairs)
     for Ls in (300, 2500, 9000):                                                              # short company
         ref = synth.random_seq(rng, Ls)
