@@ -533,23 +533,31 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
             const bool chain_bound = !by_len.empty() && (double)(b->tasks[(size_t)by_len[0]].qlen + b->tasks[(size_t)by_len[0]].tlen) * 1.3e-6 > 2.0 * t_thr;
             const int pct = b->pages_total > b->cap_pages && !chain_bound ? std::min(c->segment_pool_pct, c->segment_pool_pct_bound) : c->segment_pool_pct;
             int64_t pages = 0, longest_in = 0, longest_out = 0;
-            for (int32_t ti : by_len) {
-                const DevTask& d = b->tasks[(size_t)ti];
-                const int64_t n_diag = (int64_t)d.qlen + d.tlen - 1;
-                const int64_t rpp = d.rows_per_page;
-                const int64_t warm = (int64_t)c->segment_warm_pct * d.w / 100 + 1024;                    // generous: a flat cold start is bit-identical well within it (fallback if not)
-                const int64_t want = c->segment_rows > 0 ? c->segment_rows : std::max<int64_t>(4 * warm, 16384);
-                const int64_t seg_rows = std::max<int64_t>(1, (want + rpp - 1) / rpp) * rpp;      // whole pages
-                const int n_segs = (int)((n_diag + seg_rows - 1) / seg_rows);
-                if (n_segs < 2 || seg_rows < 2 * warm) continue;
-                if ((pages + d.tb_pages) * 100 > b->cap_pages * pct) { longest_out = std::max(longest_out, n_diag); continue; }
-                pages += d.tb_pages; longest_in = std::max(longest_in, n_diag);
-                plan.push_back({ti, seg_rows, warm, n_segs});
+            // segments of 4 x warm rows cost 25 % more cells; if that leaves most SMs without a segment (a handful of long
+            // tasks: cfg1's two contigs make 16), halve them: 2 x warm rows, 50 % more cells on SMs that would idle anyway
+            int total_segs = 0;
+            for (int mult = 4; mult >= 2; mult -= 2) {
+                plan.clear(); pages = longest_in = longest_out = 0; total_segs = 0;
+                for (int32_t ti : by_len) {
+                    const DevTask& d = b->tasks[(size_t)ti];
+                    const int64_t n_diag = (int64_t)d.qlen + d.tlen - 1;
+                    const int64_t rpp = d.rows_per_page;
+                    const int64_t warm = (int64_t)c->segment_warm_pct * d.w / 100 + 1024;                    // generous: a flat cold start is bit-identical well within it (fallback if not)
+                    const int64_t want = c->segment_rows > 0 ? c->segment_rows : std::max<int64_t>(mult * warm, 16384);
+                    const int64_t seg_rows = std::max<int64_t>(1, (want + rpp - 1) / rpp) * rpp;      // whole pages
+                    const int n_segs = (int)((n_diag + seg_rows - 1) / seg_rows);
+                    if (n_segs < 2 || seg_rows < 2 * warm) continue;
+                    if ((pages + d.tb_pages) * 100 > b->cap_pages * pct) { longest_out = std::max(longest_out, n_diag); continue; }
+                    pages += d.tb_pages; longest_in = std::max(longest_in, n_diag);
+                    plan.push_back({ti, seg_rows, warm, n_segs});
+                    total_segs += n_segs;
+                }
+                if (c->segment_rows > 0 || total_segs >= c->sm_count) break;
             }
             const size_t planned = plan.size();
             if (getenv("FSV_TRACE"))
-                fprintf(stderr, "[fsv] segment plan: min_diags %lld, eligible %zu, within the pool share (%d %%) %zu (%lld pages of %lld), longest in %lld / left whole %lld -> %zu tasks segmented\n",
-                        (long long)min_diags, by_len.size(), pct, planned, (long long)pages, (long long)b->cap_pages, (long long)longest_in, (long long)longest_out, plan.size());
+                fprintf(stderr, "[fsv] segment plan: min_diags %lld, eligible %zu, within the pool share (%d %%) %zu (%lld pages of %lld), longest in %lld / left whole %lld -> %zu tasks in %d segments\n",
+                        (long long)min_diags, by_len.size(), pct, planned, (long long)pages, (long long)b->cap_pages, (long long)longest_in, (long long)longest_out, plan.size(), total_segs);
         }
         for (const SegPlan& sp : plan) {
             const int32_t ti = sp.ti;
@@ -673,7 +681,7 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
         DEV(d_seg_tasks, sz_seg[1], b->seg_tasks.size() * sizeof(SegTask));
         DEV(d_seg_tables, sz_seg[2], b->seg_pages.size() * 4 + 16);
         DEV(d_seg_work, sz_seg[3], b->seg_work.size() * 4 + 16);
-        DEV(d_seg_done, sz_seg[4], b->seg_tasks.size() * 4 + 16);
+        DEV(d_seg_done, sz_seg[4], b->seg_tasks.size() * 8 + 16);      // done counters, then cancel flags
         DEV(d_seg_foot, sz_seg[5], b->segs.size() * 4 + 16);
         DEV(d_seg_rec, sz_seg[6], (size_t)b->seg_rec_total * sizeof(int4) + 16);
         DEV(d_seg_snap, sz_seg[7], (size_t)b->seg_snap_words * 4 + 16);
@@ -749,7 +757,7 @@ extern "C" int fsv_batch_run(fsv_batch* b)
             memcpy(&ctrl[8 + 2 * (b->launches.size() + i)], &st, 8);
         }
         if (!b->segs.empty()) {
-            CK(c, cudaMemsetAsync(b->d_seg_done, 0, b->seg_tasks.size() * 4, c->stream));
+            CK(c, cudaMemsetAsync(b->d_seg_done, 0, b->seg_tasks.size() * 8, c->stream));
             CK(c, cudaMemsetAsync(b->d_seg_foot, 0xff, b->segs.size() * 4, c->stream));
             CK(c, cudaMemsetAsync(b->d_seg_snap, 0, (size_t)b->seg_snap_words * 4, c->stream));
         }
@@ -775,7 +783,7 @@ extern "C" int fsv_batch_run(fsv_batch* b)
     R.timeline = b->d_timeline;
     R.sc = b->sc;
     R.segs = b->d_segs; R.seg_tasks = b->d_seg_tasks; R.seg_rec = b->d_seg_rec; R.seg_snap = b->d_seg_snap;
-    R.seg_tables = b->d_seg_tables; R.seg_done = b->d_seg_done; R.seg_foot = b->d_seg_foot;
+    R.seg_tables = b->d_seg_tables; R.seg_done = b->d_seg_done; R.seg_cancel = b->d_seg_done + b->seg_tasks.size(); R.seg_foot = b->d_seg_foot;
 
     cudaEvent_t e0, e1;
     CK(c, cudaEventCreate(&e0)); CK(c, cudaEventCreate(&e1));

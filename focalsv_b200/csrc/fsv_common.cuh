@@ -335,6 +335,7 @@ struct RunCtx {
     uint32_t* seg_snap;
     const int32_t* seg_tables;
     int32_t* seg_done;           // per segmented task: segments finished
+    int32_t* seg_cancel;         // per segmented task: set by segment 0 when the alignment z-drops inside it; the other segments poll it and stop
     int32_t* seg_foot;           // per segment: antidiagonal at which the band ran out inside it, or -1
 };
 

@@ -321,6 +321,10 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
         constexpr bool wild = decltype(wild_c)::value;
         for (int r = rz;; ++r) {
             const int par = r & 1, ppar = par ^ 1;
+            // a later segment of a task that z-dropped inside segment 0: stop through the same flag a z-drop uses (posted at
+            // iteration r, seen by every thread in section (A) of iteration r+1)
+            if (SEG && segmode && G.index > 0 && (r & 255) == 0 && r > rz + 1 && tid == 0 && __ldcg(C.seg_cancel + T.seg_id) != 0)
+                sts32(sb + OFF_STOP, (uint32_t)r);
             const int s3m1 = s3 == 0 ? 2 : s3 - 1, s3m2 = s3 == 2 ? 0 : s3 + 1;   // (r-1)%3, (r-2)%3
 
             // ---- neighbour's lane 15 as it stood after the previous antidiagonal
@@ -374,15 +378,24 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                 if (SEG && segmode) {
                     // a segment only RECORDS its own antidiagonals (scores relative to its own cold start): the
                     // bookkeeping is replayed over the whole task once every boundary has been checked
-                    if (warp == 0 && lane == 0 && d >= r_own) {
+                    if (warp == 0 && d >= r_own && !dropped) {
                         int st0d, en0d;
                         band_limits(d, qlen, tlen, w, st0d, en0d);
                         int max_t = en0d;
                         const uint32_t bk = lds32(sb + OFF_KEY + 4u * s3m2);
                         if (bk != 0) max_t = (int)((bk - 1u) & ((1u << 26) - 1u));
-                        const int32_t hen0 = en0d == tlen - 1 ? (int32_t)lds32(sb + OFF_HEN0 + 4u * s3m2) : FSV_NEG_INF;
-                        const int32_t hst0 = d - st0d == qlen - 1 ? (int32_t)lds32(sb + OFF_HST0 + 4u * s3m2) : FSV_NEG_INF;
-                        C.seg_rec[C.seg_tasks[T.seg_id].rec_off + d] = make_int4(M2, max_t, hen0, hst0);
+                        if (lane == 0) {
+                            const int32_t hen0 = en0d == tlen - 1 ? (int32_t)lds32(sb + OFF_HEN0 + 4u * s3m2) : FSV_NEG_INF;
+                            const int32_t hst0 = d - st0d == qlen - 1 ? (int32_t)lds32(sb + OFF_HST0 + 4u * s3m2) : FSV_NEG_INF;
+                            C.seg_rec[C.seg_tasks[T.seg_id].rec_off + d] = make_int4(M2, max_t, hen0, hst0);
+                        }
+                        // segment 0 starts from the true state, so while the alignment is inside it the running maximum IS known:
+                        // a z-drop here ends the task (the stitch's replay finds it again in the records) - the later segments
+                        // would only be wasted work, and they are what a short batch would wait for: tell them to stop
+                        if (G.index == 0 && ez.apply_zdrop(M2, d, max_t, T.zdrop, sc.e_drop)) {
+                            dropped = true;
+                            if (lane == 0) { sts32(sb + OFF_STOP, (uint32_t)r); atomicExch(C.seg_cancel + T.seg_id, 1); }
+                        }
                     }
                 } else
                 if (warp == 0 && !dropped) {
