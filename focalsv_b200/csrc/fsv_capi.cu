@@ -60,7 +60,7 @@ struct fsv_ctx {
     int segment_extz = 1;            // auto mode: 1 = extension (EXTZ_ONLY) tasks are segmented too, 0 = global tasks only
     int segment_pool_pct_bound = 25; // the same share when the batch's traceback does not fit the pool
     int segment_pool_pct = 45;       // share of the traceback pool the segmented tasks' static pages may take
-    int64_t segment_rows = 0;        // target antidiagonals per segment, rounded up to whole traceback pages (0 = auto: 4 x warm-up)
+    int64_t segment_rows = 0;        // target antidiagonals per segment, rounded up to 1024 (0 = auto: 4 x or 2 x the warm-up)
     int lazy_min_pages = 16;    // DPX tasks with at least this many traceback pages take them as they advance (0 = all up front)
     int pool_stall_ms = 60000;  // lazy-pool watchdog
     int lazy_fill_pct = 65;     // admission of such a task waits while the projected peak of those running exceeds this share of the pool
@@ -541,10 +541,9 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
                 for (int32_t ti : by_len) {
                     const DevTask& d = b->tasks[(size_t)ti];
                     const int64_t n_diag = (int64_t)d.qlen + d.tlen - 1;
-                    const int64_t rpp = d.rows_per_page;
                     const int64_t warm = (int64_t)c->segment_warm_pct * d.w / 100 + 1024;                    // generous: a flat cold start is bit-identical well within it (fallback if not)
                     const int64_t want = c->segment_rows > 0 ? c->segment_rows : std::max<int64_t>(mult * warm, 16384);
-                    const int64_t seg_rows = std::max<int64_t>(1, (want + rpp - 1) / rpp) * rpp;      // whole pages
+                    const int64_t seg_rows = (want + 1023) / 1024 * 1024;      // (the task's pages are static, so segments need not own whole pages)
                     const int n_segs = (int)((n_diag + seg_rows - 1) / seg_rows);
                     if (n_segs < 2 || seg_rows < 2 * warm) continue;
                     if ((pages + d.tb_pages) * 100 > b->cap_pages * pct) { longest_out = std::max(longest_out, n_diag); continue; }

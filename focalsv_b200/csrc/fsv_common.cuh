@@ -289,7 +289,7 @@ __device__ inline int queue_take(const TaskQueue& Q, int end)
 
 // ---------------------------------------------------------------------------
 // Segmented tasks.  The difference recurrence forgets its start after about 2w antidiagonals (DESIGN.md section 6,
-// scripts/convergence_probe.py), so a long task is cut into segments of whole traceback pages that run on
+// scripts/convergence_probe.py), so a long task is cut into segments (rows of a static page table, so they may share pages) that run on
 // different CTAs at the same time: segment s > 0 starts COLD `warm` antidiagonals before its first own row, writes
 // traceback rows and one record per antidiagonal from its first own row on, and dumps its state at its first and
 // last own rows.  The CTA that finishes the task's last segment checks every boundary bit for bit (the state a

@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
         const uint8_t* query = C.qarena + T.q_off;
         const uint8_t* target = C.tarena + T.t_off;
         // traceback rows live in pool pages: row r is in page r / rows_per_page
-        int tb_rip = 0, tb_pg = SEG ? r_own / T.rows_per_page : 0;     // row inside the current page, page number (segments own whole pages)
+        int tb_rip = SEG ? r_own % T.rows_per_page : 0, tb_pg = SEG ? r_own / T.rows_per_page : 0;     // row inside the current page, page number (a segmented task's pages are static: segments may share one)
         uint8_t* tb_page = TB ? C.pool.base + (int64_t)table[tb_pg] * C.pool.page_bytes : nullptr;
         const int n_diag = qlen + tlen - 1;
 
