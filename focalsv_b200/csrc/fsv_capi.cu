@@ -57,6 +57,8 @@ struct fsv_ctx {
     int64_t segment_min_diags = -1;  // tasks with at least this many antidiagonals are cut into segments (0 = off, -1 = auto:
                                      // those whose chain of antidiagonals would outlast 60 % of the batch's throughput time)
     int segment_warm_pct = 400;      // cold-start lead of a segment, in percent of the band width (+1024 antidiagonals)
+    int segment_slots = 1;           // 1 = long tasks beyond the pool share re-use the static pages of earlier ones (in turn), 0 = they stay whole
+    int segment_align_pages = 1;     // 1 = segments are whole traceback pages, 0 = any multiple of 1024 antidiagonals
     int segment_extz = 1;            // auto mode: 1 = extension (EXTZ_ONLY) tasks are segmented too, 0 = global tasks only
     int segment_pool_pct_bound = 25; // the same share when the batch's traceback does not fit the pool
     int segment_pool_pct = 45;       // share of the traceback pool the segmented tasks' static pages may take
@@ -249,6 +251,8 @@ extern "C" int fsv_set_option(fsv_ctx* c, const char* key, int64_t value)
     }
     if (!strcmp(key, "segment_min_diags")) { if (value < -1) return FSV_ERR_INVALID; c->segment_min_diags = value; return FSV_OK; }
     if (!strcmp(key, "segment_warm_pct")) { if (value < 50 || value > 2000) return FSV_ERR_INVALID; c->segment_warm_pct = (int)value; return FSV_OK; }
+    if (!strcmp(key, "segment_slots")) { c->segment_slots = value != 0; return FSV_OK; }
+    if (!strcmp(key, "segment_align_pages")) { c->segment_align_pages = value != 0; return FSV_OK; }
     if (!strcmp(key, "segment_extz")) { c->segment_extz = value != 0; return FSV_OK; }
     if (!strcmp(key, "segment_pool_pct_bound")) { if (value < 1 || value > 90) return FSV_ERR_INVALID; c->segment_pool_pct_bound = (int)value; return FSV_OK; }
     if (!strcmp(key, "segment_pool_pct")) { if (value < 1 || value > 90) return FSV_ERR_INVALID; c->segment_pool_pct = (int)value; return FSV_OK; }
@@ -523,7 +527,13 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
         }
         std::stable_sort(by_len.begin(), by_len.end(), [&](int32_t a, int32_t x) { return b->tasks[a].qlen + b->tasks[a].tlen > b->tasks[x].qlen + b->tasks[x].tlen; });
         std::vector<std::vector<int32_t>> per_nw(9);
-        struct SegPlan { int32_t ti; int64_t seg_rows, warm; int n_segs; };
+        struct SegPlan { int32_t ti; int64_t seg_rows, warm; int n_segs; int slot; };
+        // The static region is a few SLOTS: the longest tasks get one each while the pool share lasts, the next ones re-use the slot
+        // of an earlier task of the same warp class (same work queue, so that task's segments were all taken before theirs) and
+        // wait on the device for its stitch to end.  A batch with many long tasks then works through them a few at a time, every
+        // SM on their segments, instead of leaving all but the first few whole.
+        struct SegSlot { int64_t base, size; int nw, users, last_user, first_table_off; };
+        std::vector<SegSlot> slots;
         std::vector<SegPlan> plan;
         {
             // static pages: a share of the pool; smaller when the batch's traceback does not fit the pool anyway (then the
@@ -537,23 +547,43 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
             // tasks: cfg1's two contigs make 16), halve them: 2 x warm rows, 50 % more cells on SMs that would idle anyway
             int total_segs = 0;
             for (int mult = 4; mult >= 2; mult -= 2) {
-                plan.clear(); pages = longest_in = longest_out = 0; total_segs = 0;
+                plan.clear(); slots.clear(); pages = longest_in = longest_out = 0; total_segs = 0;
                 for (int32_t ti : by_len) {
                     const DevTask& d = b->tasks[(size_t)ti];
                     const int64_t n_diag = (int64_t)d.qlen + d.tlen - 1;
                     const int64_t warm = (int64_t)c->segment_warm_pct * d.w / 100 + 1024;                    // generous: a flat cold start is bit-identical well within it (fallback if not)
                     const int64_t want = c->segment_rows > 0 ? c->segment_rows : std::max<int64_t>(mult * warm, 16384);
-                    const int64_t seg_rows = (want + 1023) / 1024 * 1024;      // (the task's pages are static, so segments need not own whole pages)
+                    // whole pages by default.  (The pages are static, so segments could share them: `segment_align_pages` 0 cuts narrow-band
+                    // tasks four times finer - cfg3's reads 146 -> 74 ms, cfg1's 50 -> 32 ms - but with that many more boundaries some
+                    // fail their check and the whole-task fallback costs more than was won: off until a failed boundary is cheap.)
+                    const int64_t rpp = d.rows_per_page;
+                    const int64_t seg_rows = c->segment_align_pages ? std::max<int64_t>(1, (want + rpp - 1) / rpp) * rpp : (want + 1023) / 1024 * 1024;
                     const int n_segs = (int)((n_diag + seg_rows - 1) / seg_rows);
                     if (n_segs < 2 || seg_rows < 2 * warm) continue;
-                    if ((pages + d.tb_pages) * 100 > b->cap_pages * pct) { longest_out = std::max(longest_out, n_diag); continue; }
-                    pages += d.tb_pages; longest_in = std::max(longest_in, n_diag);
-                    plan.push_back({ti, seg_rows, warm, n_segs});
+                    int slot = -1;
+                    if ((pages + d.tb_pages) * 100 <= b->cap_pages * pct) {
+                        slot = (int)slots.size();
+                        slots.push_back({pages, d.tb_pages, d.nw, 0, -1, -1});
+                        pages += d.tb_pages;
+                    } else if (c->segment_slots && (double)n_diag * 1.3e-6 > 2.0 * t_thr) {
+                        // (only chains the batch cannot hide anyway: re-using slots for every eligible task makes the medium ones queue
+                        // behind each other's stitch while they could have run whole side by side - cfg4 at 1/4 scale 840 -> 1 515 ms)
+                        for (size_t k = 0; k < slots.size(); ++k)
+                            if (slots[k].nw == d.nw && slots[k].size >= d.tb_pages && (slot < 0 || slots[k].users < slots[(size_t)slot].users)) slot = (int)k;
+                    }
+                    if (slot < 0) { longest_out = std::max(longest_out, n_diag); continue; }
+                    ++slots[(size_t)slot].users;
+                    longest_in = std::max(longest_in, n_diag);
+                    plan.push_back({ti, seg_rows, warm, n_segs, slot});
                     total_segs += n_segs;
                 }
                 if (c->segment_rows > 0 || total_segs >= c->sm_count) break;
             }
             const size_t planned = plan.size();
+            // a chain-bound batch still waits for the longest task that stays WHOLE: if the pool share ran out before the chains got
+            // markedly shorter, the segments only take pages away from it (full-size cfg4, 9.4 M-antidiagonal tasks of 29 GB each:
+            // 18.1 s whole, 22.3 s with three tasks segmented, 38 s with four) - leave every task whole
+            if (c->segment_min_diags < 0 && chain_bound && longest_out * 10 > longest_in * 7) { plan.clear(); slots.clear(); total_segs = 0; }
             if (getenv("FSV_TRACE"))
                 fprintf(stderr, "[fsv] segment plan: min_diags %lld, eligible %zu, within the pool share (%d %%) %zu (%lld pages of %lld), longest in %lld / left whole %lld -> %zu tasks in %d segments\n",
                         (long long)min_diags, by_len.size(), pct, planned, (long long)pages, (long long)b->cap_pages, (long long)longest_in, (long long)longest_out, plan.size(), total_segs);
@@ -569,8 +599,11 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
             st.n_segs = n_segs; st.first_seg = (int32_t)b->segs.size();
             b->seg_rec_total += n_diag;
             b->seg_snap_words += (int64_t)2 * (n_segs - 1) * SEG_SNAP_WORDS;
-            for (int pg = 0; pg < d.tb_pages; ++pg) b->seg_pages.push_back((int32_t)(b->pool_pages - 1 - (b->seg_static_pages + pg)));
-            b->seg_static_pages += d.tb_pages;
+            SegSlot& sl = slots[(size_t)sp.slot];
+            for (int pg = 0; pg < d.tb_pages; ++pg) b->seg_pages.push_back((int32_t)(b->pool_pages - 1 - (sl.base + pg)));
+            if (sl.first_table_off < 0) sl.first_table_off = st.table_off;      // the first user's table lists the whole slot
+            st.wait_for = sl.last_user; st.free_table_off = 0; st.free_pages = 0;
+            sl.last_user = (int)b->seg_tasks.size();
             d.seg_id = (int32_t)b->seg_tasks.size();
             for (int k = 0; k < n_segs; ++k) {
                 DevSeg g{};
@@ -582,6 +615,11 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
             }
             b->seg_tasks.push_back(st);
             is_seg[(size_t)ti] = 1;
+        }
+        for (const SegSlot& sl : slots) if (sl.last_user >= 0) {
+            b->seg_tasks[(size_t)sl.last_user].free_table_off = sl.first_table_off;
+            b->seg_tasks[(size_t)sl.last_user].free_pages = (int32_t)sl.size;
+            b->seg_static_pages += sl.size;
         }
         for (int nw = 8; nw >= 1; --nw) if (!per_nw[(size_t)nw].empty()) {
             b->seg_launches.push_back({nw, (int)b->seg_work.size(), (int)per_nw[(size_t)nw].size()});
@@ -680,7 +718,7 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
         DEV(d_seg_tasks, sz_seg[1], b->seg_tasks.size() * sizeof(SegTask));
         DEV(d_seg_tables, sz_seg[2], b->seg_pages.size() * 4 + 16);
         DEV(d_seg_work, sz_seg[3], b->seg_work.size() * 4 + 16);
-        DEV(d_seg_done, sz_seg[4], b->seg_tasks.size() * 8 + 16);      // done counters, then cancel flags
+        DEV(d_seg_done, sz_seg[4], b->seg_tasks.size() * 12 + 16);      // done counters, cancel flags, released flags
         DEV(d_seg_foot, sz_seg[5], b->segs.size() * 4 + 16);
         DEV(d_seg_rec, sz_seg[6], (size_t)b->seg_rec_total * sizeof(int4) + 16);
         DEV(d_seg_snap, sz_seg[7], (size_t)b->seg_snap_words * 4 + 16);
@@ -756,7 +794,7 @@ extern "C" int fsv_batch_run(fsv_batch* b)
             memcpy(&ctrl[8 + 2 * (b->launches.size() + i)], &st, 8);
         }
         if (!b->segs.empty()) {
-            CK(c, cudaMemsetAsync(b->d_seg_done, 0, b->seg_tasks.size() * 8, c->stream));
+            CK(c, cudaMemsetAsync(b->d_seg_done, 0, b->seg_tasks.size() * 12, c->stream));
             CK(c, cudaMemsetAsync(b->d_seg_foot, 0xff, b->segs.size() * 4, c->stream));
             CK(c, cudaMemsetAsync(b->d_seg_snap, 0, (size_t)b->seg_snap_words * 4, c->stream));
         }
@@ -782,7 +820,7 @@ extern "C" int fsv_batch_run(fsv_batch* b)
     R.timeline = b->d_timeline;
     R.sc = b->sc;
     R.segs = b->d_segs; R.seg_tasks = b->d_seg_tasks; R.seg_rec = b->d_seg_rec; R.seg_snap = b->d_seg_snap;
-    R.seg_tables = b->d_seg_tables; R.seg_done = b->d_seg_done; R.seg_cancel = b->d_seg_done + b->seg_tasks.size(); R.seg_foot = b->d_seg_foot;
+    R.seg_tables = b->d_seg_tables; R.seg_done = b->d_seg_done; R.seg_cancel = b->d_seg_done + b->seg_tasks.size(); R.seg_released = b->d_seg_done + 2 * b->seg_tasks.size(); R.seg_foot = b->d_seg_foot;
 
     cudaEvent_t e0, e1;
     CK(c, cudaEventCreate(&e0)); CK(c, cudaEventCreate(&e1));

@@ -306,7 +306,9 @@ struct SegTask {
     int64_t snap_off;           // into seg_snap (words): boundary b = slots 2b (last row of segment b) and 2b+1 (warm end of b+1)
     int32_t table_off;          // into seg_tables: the task's page table (static pages, all rows)
     int32_t n_segs, first_seg;
-    int32_t pad_;
+    int32_t wait_for;           // the segmented task that used this task's static pages before it (its segments wait for that one's
+                                // stitch to end), or -1: the static region is a few SLOTS that the long tasks of a warp class take turns in
+    int32_t free_table_off, free_pages;   // last user of a slot: the slot's pages, returned to the dynamic pool after the stitch (else 0)
 };
 constexpr int SEG_SNAP_HDR = 8;                 // words: anchor H (lane st0), valid flag
 constexpr int SEG_SNAP_PER_THREAD = 67;         // 64 state words, Vt, Hb, reserved
@@ -335,6 +337,7 @@ struct RunCtx {
     uint32_t* seg_snap;
     const int32_t* seg_tables;
     int32_t* seg_done;           // per segmented task: segments finished
+    int32_t* seg_released;       // per segmented task: its stitch is over and its static pages may be written by the slot's next user
     int32_t* seg_cancel;         // per segmented task: set by segment 0 when the alignment z-drops inside it; the other segments poll it and stop
     int32_t* seg_foot;           // per segment: antidiagonal at which the band ran out inside it, or -1
 };

@@ -230,6 +230,15 @@ __device__ __forceinline__ void dpx_cells(uint32_t (&U)[8], uint32_t (&V)[8], ui
 // shared memory reserved, so that a CTA working on one of the few very long tasks has its SM to itself.
 // TBM: 0 = score only, 1 = traceback, ties to the left (default), 2 = traceback, ties to the right (KSW_EZ_RIGHT),
 // 3 = score only with KSW_EZ_APPROX_MAX (:270-286): no H[] at all, one cell is followed greedily.
+// End of a segmented task (one thread): the slot's next user may start; the slot's LAST user returns its pages to the dynamic pool.
+__device__ __forceinline__ void seg_release(const RunCtx& C, int seg_id)
+{
+    const SegTask ST = C.seg_tasks[seg_id];
+    if (ST.free_pages > 0) pool_free(C.pool, ST.free_pages, const_cast<int32_t*>(C.seg_tables) + ST.free_table_off);
+    __threadfence();
+    atomicExch(C.seg_released + seg_id, 1);
+}
+
 // SEG: the launch works on SEGMENTS of long tasks (fsv_common.cuh, DevSeg): P.Q holds segment indices.
 template <bool DUAL, int TBM, int NW, bool EXCL = false, bool SEG = false>
 __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kernel(const __grid_constant__ DpxParams P)
@@ -280,6 +289,15 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
         const DevTask T = C.tasks[ti];
         const bool segmode = SEG && seg_redo < 0;
         if (SEG) { table = const_cast<int32_t*>(C.seg_tables) + C.seg_tasks[T.seg_id].table_off; seg_redo = -1; }
+        if (SEG && segmode) {
+            // the task's static pages are a slot an earlier task of this queue may still be reading (its CIGAR walk): wait for
+            // that task's stitch.  Its segments were all taken from this queue before this one, so they are running or done.
+            const int wf = C.seg_tasks[T.seg_id].wait_for;
+            if (wf >= 0) {
+                if (tid == 0) { unsigned ns = 256; while (__ldcg(C.seg_released + wf) == 0) { __nanosleep(ns); if (ns < 8192) ns <<= 1; } __threadfence(); }
+                __syncthreads();
+            }
+        }
         const int rz = segmode ? G.r0 : 0;                                 // first antidiagonal computed
         const int r_own = segmode ? G.r_begin : 0;                         // first antidiagonal whose results count
         if (tid == 0 && C.timeline && (!SEG || G.index == 0)) C.timeline[2 * T.orig] = global_ns();
@@ -887,7 +905,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
             if (warp == 0) finish_task(C, T, table, e2, cells2, TB);
             __syncthreads();
             if (tid == 0) {
-                pool_free(C.pool, T.tb_pages, table);      // the task's static pages join the dynamic pool
+                seg_release(C, T.seg_id);
                 if (C.timeline) C.timeline[2 * T.orig + 1] = global_ns();
             }
             continue;
@@ -899,7 +917,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
         if (tid == 0) {
             const bool lazy = C.pool.lazy && C.pool.lazy_min_pages > 0 && T.tb_pages >= C.pool.lazy_min_pages;      // as task_pages decided
             if (!SEG) pool_free(C.pool, (int)lds32(sb + OFF_HELD), table, lazy ? C.slot_base + (int)blockIdx.x : -1);
-            else pool_free(C.pool, T.tb_pages, table);      // (re-run of a segmented task) its static pages join the dynamic pool
+            else seg_release(C, T.seg_id);                  // (re-run of a segmented task)
             if (C.timeline) C.timeline[2 * T.orig + 1] = global_ns();
         }
     }

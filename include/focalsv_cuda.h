@@ -138,6 +138,9 @@ int fsv_get_stats(const fsv_ctx* ctx, fsv_stats* out);
  *   "segment_rows"            antidiagonals per segment (0 = auto: 4 x the cold-start lead, whole traceback pages)
  *   "segment_warm_pct"        cold-start lead of a segment in percent of the band width (default 400: 2w to forget the start, 2w more until every lane of the band entered after that; 250 still verifies on the probes, 200 does not)
  *   "segment_pool_pct"        share of the traceback pool the segmented tasks may hold (default 45)
+ *   "segment_slots"           1 = long tasks beyond the pool share re-use the static pages of earlier ones in turn (default), 0 = they stay whole
+ *   "segment_align_pages"     1 = segments are whole traceback pages (default), 0 = any multiple of 1024 antidiagonals (experiment)
+ *   "segment_pool_pct_bound"  the pool share when the batch's traceback does not fit the pool and it is throughput-bound (default 25)
  *   "segment_extz"            auto mode: 1 = extension (EXTZ_ONLY) tasks are segmented too (default), 0 = global tasks only
  *   "force_exact"             1 = int8-exact general kernel only
  *   "exact_smem_lanes", "force_excl"   kernel experiments */
