@@ -381,6 +381,39 @@ def test_segmented_long_tasks(oracle, preset, w):
         al.close()
 
 
+def test_segment_slots_are_reused(oracle):
+    """More long tasks than the static pool share holds: the later ones re-use the pages of earlier ones in turn
+    (fsv_common.cuh, SegTask::wait_for) and their segments wait on the device for the previous user's stitch."""
+    from focalsv_b200 import api
+    from focalsv_b200.presets import PRESETS
+    rng = np.random.default_rng(4242)
+    pairs, flags = [], []
+    for i in range(7):
+        L = 70000 - 3000 * i
+        ref = synth.random_seq(rng, L)
+        q, _ = synth.plant_svs(rng, ref, 4, max_net=180, max_len=170)
+        pairs.append((synth.mutate(rng, q, 0.001, 0.0003, 0.0003), ref)); flags.append(_abi.EZ_EXTZ_ONLY if i == 3 else 0)
+    for Ls in (400, 3000):
+        ref = synth.random_seq(rng, Ls)
+        pairs.append((synth.mutate(rng, ref, 0.01, 0.004, 0.004), ref)); flags.append(0)
+    g = synth._pack("slots", "hifiasm", pairs, 500, PRESETS["hifiasm"].zdrop, flags=np.array(flags, dtype=np.int32))
+    al = api.Aligner(0)
+    try:
+        al.set_option("traceback_budget_bytes", 20 * (32 << 20))      # 20 pages; a long task needs 3; 45 % = 9 pages = 3 slots
+        al.set_option("segment_min_diags", 50000)
+        bad, ores, gres = compare_group(oracle, al, g, threads=16)
+        assert not bad, bad
+        st = al.stats()
+        assert st["segmented_tasks"] == 7, st                          # 3 with a slot of their own, 4 re-using one
+        assert st["segment_fallbacks"] == 0, st
+        al.set_option("segment_slots", 0)
+        bad, _, _ = compare_group(oracle, al, g, threads=16)
+        assert not bad, bad
+        assert al.stats()["segmented_tasks"] == 3
+    finally:
+        al.close()
+
+
 def test_mixed_kernel_variants_share_the_pool(oracle, aligner):
     """One batch whose tasks land on several kernel variants at once (1/2/4-warp DPX classes, score-only and
     CIGAR, wildcard tasks, and right-aligned tasks on the general kernel), all running concurrently on one page pool."""
