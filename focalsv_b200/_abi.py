@@ -45,7 +45,8 @@ SIGNATURE_DTYPE = np.dtype([("task", "<i4"), ("svtype", "<i4"), ("pos", "<i8"), 
 PAIR_DTYPE = np.dtype([("a_off", "<i8"), ("b_off", "<i8"), ("a_len", "<i4"), ("b_len", "<i4")], align=True)
 RECORD_DTYPE = np.dtype([("pos", "<i8"), ("ref_end", "<i8"), ("cigar_off", "<i8"), ("n_cigar", "<i4"), ("query_length", "<i4"),
                          ("score", "<i4"), ("zdropped", "<i4"), ("is_reverse", "<i4"), ("mapq", "<i4")], align=True)
-assert RECORD_DTYPE.itemsize == 48
+PIECE_DTYPE = np.dtype([("q_beg", "<i4"), ("q_end", "<i4"), ("t_beg", "<i4"), ("t_end", "<i4")], align=True)
+assert RECORD_DTYPE.itemsize == 48 and PIECE_DTYPE.itemsize == 16
 assert TASK_DTYPE.itemsize == 40 and RESULT_DTYPE.itemsize == 64 and SIGNATURE_DTYPE.itemsize == 32 and PAIR_DTYPE.itemsize == 24
 
 # fields that must be bit-identical to ksw_extz_t (ksw2.h:23-32)

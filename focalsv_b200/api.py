@@ -21,7 +21,7 @@ EXPORTS = ("fsv_init", "fsv_destroy", "fsv_strerror", "fsv_last_error", "fsv_abi
            "fsv_get_stats", "fsv_set_option", "fsv_align_batch", "fsv_batch_create", "fsv_batch_run",
            "fsv_batch_fetch", "fsv_batch_destroy", "fsv_ksw_extz2", "fsv_ksw_extd2", "fsv_task_cells",
            "fsv_lpt_bins", "fsv_measure_int_peak", "fsv_batch_timeline", "fsv_batch_signatures", "fsv_edit_distance_batch",
-           "fsv_preset_lookup", "fsv_realign_regions")
+           "fsv_preset_lookup", "fsv_realign_regions", "fsv_chain_pieces")
 
 _lib = None
 
@@ -61,6 +61,8 @@ def load_library(path=None):
     lib.fsv_batch_signatures.argtypes = [vp, vp, C.c_int, vp, sz, C.POINTER(sz)]
     lib.fsv_edit_distance_batch.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp]
     lib.fsv_batch_destroy.restype = None
+    lib.fsv_chain_pieces.argtypes = [vp, i32, vp, i32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, sz, C.POINTER(sz),
+                                     C.POINTER(i32), C.POINTER(i32)]
     lib.fsv_preset_lookup.argtypes = [C.c_char_p, C.POINTER(_abi.PresetC), C.POINTER(Scoring)]
     lib.fsv_realign_regions.argtypes = [vp, vp, sz, vp, vp, vp, sz, vp, vp, sz, C.c_char_p, C.c_int, C.c_int, vp, vp, sz, C.POINTER(sz)]
     lib.fsv_task_cells.argtypes = [i32, i32, i32]
@@ -82,6 +84,25 @@ def preset_lookup(name):
     if rc != 0:
         raise FsvError(rc, "unknown preset %r" % name)
     return {k: getattr(p, k) for k, _ in _abi.PresetC._fields_[1:]}, sc
+
+
+def chain_pieces(query, target, k=19, w=19, max_occ=50, max_gap=100000, min_fill=200):
+    """fsv_chain_pieces (host only): minimizer seeding + chaining + decomposition of one (query, target) pair of code
+    arrays into the DP pieces minimap2's mm_align1 would fill.  Returns (pieces[PIECE_DTYPE], chain_score, n_anchors)."""
+    lib = load_library()
+    q = np.ascontiguousarray(query, dtype=np.uint8); t = np.ascontiguousarray(target, dtype=np.uint8)
+    cap = 1024
+    while True:
+        out = np.zeros(cap, dtype=_abi.PIECE_DTYPE)
+        n = C.c_size_t(0); sc = C.c_int32(0); na = C.c_int32(0)
+        rc = lib.fsv_chain_pieces(q.ctypes.data, q.size, t.ctypes.data, t.size, k, w, max_occ, max_gap, min_fill,
+                                  out.ctypes.data, cap, C.byref(n), C.byref(sc), C.byref(na))
+        if rc == _abi.ERR_CIGAR_CAP:
+            cap = int(n.value) + 16
+            continue
+        if rc != 0:
+            raise FsvError(rc, lib.fsv_strerror(rc).decode())
+        return out[:n.value], sc.value, na.value
 
 
 def task_cells(qlen, tlen, w):

@@ -34,7 +34,7 @@ def stale():
 
 
 def _units(defs):
-    units = [("capi", os.path.join(CSRC, "fsv_capi.cu"), [])]
+    units = [("capi", os.path.join(CSRC, "fsv_capi.cu"), []), ("chain", os.path.join(CSRC, "fsv_chain.cu"), [])]
     for d, t in VARIANTS:
         units.append(("dpx_%d%d" % (d, t), os.path.join(CSRC, "fsv_dpx_variant.cu"),
                       ["-DFSV_VARIANT_DUAL=%d" % d, "-DFSV_VARIANT_TBM=%d" % t]))

@@ -76,6 +76,68 @@ def realign_regions_abi(aligner, ref_codes, regions, contigs, preset="asm5", bw=
     return out
 
 
+# minimap2 2.24 preset seeding parameters (-k, -w) [UNVERIFIED-EXT, SURVEY appendix B]
+SEEDING = {"asm5": (19, 19), "asm10": (19, 19), "map-hifi": (19, 19), "map-pb": (19, 10), "map-ont": (15, 10)}
+
+
+def realign_regions_chained(aligner, windows, contigs, preset="asm5", bw=2000, min_fill=200, max_occ=50):
+    """Row f2: the same (contig, window) pairs as realign_regions, but decomposed the way minimap2 decomposes them
+    before it calls ksw2 (api.chain_pieces: minimizers, chaining, cuts at anchors >= min_fill apart): every piece is a
+    small global DP task, all pieces of all pairs go to the GPU as ONE batch, and the piece CIGARs are stitched.
+    `aligner` is anything with align_batch(sc, qarena, tarena, tasks) -> (results, cigar_arena).  The result is a valid
+    global alignment of each pair; it equals minimap2's only as far as the restated seeding does (parity unpinned)."""
+    from .api import chain_pieces
+    p = PRESETS[preset]
+    sc = scoring_for(preset)
+    k, w = SEEDING[preset]
+    q = [encode(s) for _, s in contigs]
+    t = [encode(s) for _, _, s in windows]
+    q_off = np.concatenate([[0], np.cumsum([len(x) for x in q])]).astype(np.int64)
+    t_off = np.concatenate([[0], np.cumsum([len(x) for x in t])]).astype(np.int64)
+    plan, rows = [], []
+    for i in range(len(q)):
+        pcs, _, _ = chain_pieces(q[i], t[i], k, w, max_occ, p.bw_long, min_fill)
+        for pc in pcs:
+            dq, dt = int(pc["q_end"] - pc["q_beg"]), int(pc["t_end"] - pc["t_beg"])
+            ti = -1
+            if dq > 0 and dt > 0:
+                ti = len(rows)
+                rows.append((q_off[i] + int(pc["q_beg"]), t_off[i] + int(pc["t_beg"]), dq, dt, abs(dq - dt) + min(ksw_band(bw), 200)))
+            plan.append((i, dq, dt, ti))
+    tasks = np.zeros(len(rows), dtype=_abi.TASK_DTYPE)
+    if rows:
+        r = np.array(rows, dtype=np.int64)
+        tasks["q_off"], tasks["t_off"], tasks["qlen"], tasks["tlen"], tasks["w"] = r[:, 0], r[:, 1], r[:, 2], r[:, 3], r[:, 4]
+    tasks["zdrop"] = -1
+    res, arena = aligner.align_batch(sc, np.concatenate(q) if q else np.zeros(0, np.uint8),
+                                     np.concatenate(t) if t else np.zeros(0, np.uint8), tasks)
+    gap = lambda n: -min(p.q + n * p.e, p.q2 + n * p.e2) if p.q2 >= 0 else -(p.q + n * p.e)      # noqa: E731
+    cig = [[] for _ in q]
+    score = [0] * len(q)
+
+    def push(c, op, n):
+        if n <= 0:
+            return
+        if c and c[-1][0] == op:
+            c[-1] = (op, c[-1][1] + n)
+        else:
+            c.append((op, n))
+    for i, dq, dt, ti in plan:
+        if ti >= 0:
+            for op, n in cigar_tuples(task_cigar(res[ti], arena)):
+                push(cig[i], op, n)
+            score[i] += int(res[ti]["score"])
+        elif dq > 0:
+            push(cig[i], 1, dq); score[i] += gap(dq)
+        elif dt > 0:
+            push(cig[i], 2, dt); score[i] += gap(dt)
+    out = []
+    for i, ((chrom, start, _), (qname, _)) in enumerate(zip(windows, contigs)):
+        ref_span = sum(n for op, n in cig[i] if op in (0, 2))
+        out.append(AlignedContig(qname, chrom, int(start), int(start) + ref_span, cig[i], False, 60, len(q[i]), score[i], False))
+    return out
+
+
 def records_from_results(windows, contigs, res, arena):
     out = []
     for i, ((chrom, start, _), (qname, qseq)) in enumerate(zip(windows, contigs)):

@@ -253,6 +253,22 @@ int fsv_ksw_extd2(fsv_ctx* ctx, int qlen, const uint8_t* query, int tlen, const 
                   int8_t m, const int8_t* mat, int8_t q, int8_t e, int8_t q2, int8_t e2, int w,
                   int zdrop, int end_bonus, int flag, fsv_result* ez, uint32_t* cigar, int cigar_cap);
 
+/* ---- next row f2 (host only): seeding, chaining, task decomposition ------
+ * The caller of ksw2 inside `minimap2 -a -x asm5 --cs -r2k` (DipPAV_variant_call.py:103): minimap2 2.24's sketch.c /
+ * chain.c / align.c (mm_align1), a dependency that is not in the reference tree, restated from the published algorithm
+ * (PARITY UNPINNED; same strand, one chain, global ends): (w,k)-minimizers of both sequences, seeds occurring more than
+ * max_occ times dropped, colinear chaining with minimap2's gap cost, then the pair is cut at chain anchors at least
+ * min_fill bases apart.  The pieces tile [0,qlen) x [0,tlen) in order; each is one global DP task (a piece with an empty
+ * side is a pure gap), so a 200 kb x 200 kb pair becomes a few hundred small fills plus one rectangle per structural
+ * variant.  FSV_ERR_CIGAR_CAP with *n_pieces = entries needed when `cap` is too small. */
+typedef struct fsv_piece {
+    int32_t q_beg, q_end;     /* query  [q_beg, q_end) */
+    int32_t t_beg, t_end;     /* target [t_beg, t_end) */
+} fsv_piece;
+int fsv_chain_pieces(const uint8_t* query, int32_t qlen, const uint8_t* target, int32_t tlen,
+                     int k, int w, int max_occ, int max_gap, int min_fill,
+                     fsv_piece* pieces, size_t cap, size_t* n_pieces, int32_t* chain_score, int32_t* n_anchors);
+
 /* ---- roofline denominator ---------------------------------------------
  * Measured issue rate (32-bit lane-ops per second, whole device) of a dependency-free
  * stream of the instruction class the fill kernels are built from:

@@ -86,6 +86,76 @@ def test_level1_entry_point_gives_the_same_records(oracle, aligner):
         hook.realign_regions_abi(aligner, ref, regions[:1], contigs[:1], preset="no-such-preset")
 
 
+class _OracleRunner(object):
+    """align_batch on the CPU oracle: lets the host side of row f2 (seeding, chaining, stitching) be tested without a GPU."""
+    def __init__(self, O):
+        self.O = O
+
+    def align_batch(self, sc, qa, ta, tasks):
+        return self.O.run_batch(sc, qa, ta, tasks, threads=8)
+
+
+def _consumed(cigar):
+    return sum(n for op, n in cigar if op in (0, 1)), sum(n for op, n in cigar if op in (0, 2))
+
+
+def test_chain_pieces_tile_the_pair_and_isolate_the_svs():
+    from focalsv_b200 import api
+    rng = np.random.default_rng(77)
+    ref = synth.random_seq(rng, 120000)
+    q, svs = synth.plant_svs(rng, ref, 8, max_net=9000, max_len=9000)
+    q = synth.mutate(rng, q, 0.001, 0.0002, 0.0002)
+    pcs, score, n_anchor = api.chain_pieces(q, ref, 19, 19, 50, 100000, 200)
+    assert n_anchor > 5000 and score > 50000
+    assert pcs["q_beg"][0] == 0 and pcs["t_beg"][0] == 0 and pcs["q_end"][-1] == len(q) and pcs["t_end"][-1] == len(ref)
+    assert (pcs["q_beg"][1:] == pcs["q_end"][:-1]).all() and (pcs["t_beg"][1:] == pcs["t_end"][:-1]).all()
+    dq = (pcs["q_end"] - pcs["q_beg"]).astype(np.int64); dt = (pcs["t_end"] - pcs["t_beg"]).astype(np.int64)
+    assert int((dq * dt).sum()) < 0.05 * api.task_cells(len(q), len(ref), 3001)          # a small fraction of the band-3001 DP of the whole pair
+    nets = sorted(int(x) for x in (dq - dt) if abs(int(x)) >= 50)
+    want = sorted((L if t == "INS" else -L) for _, t, L in svs if L >= 50)
+    assert len(nets) == len(want) and all(abs(a - b) <= 12 for a, b in zip(nets, want)), (nets, want)
+    # degenerate inputs: nothing shared -> one piece; empty sides -> a pure gap piece
+    a = synth.random_seq(rng, 500); b = synth.random_seq(rng, 700)
+    pcs, _, n_anchor = api.chain_pieces(a, b)
+    assert n_anchor == 0 and len(pcs) == 1 and tuple(pcs[0]) == (0, 500, 0, 700)
+    pcs, _, _ = api.chain_pieces(a, np.zeros(0, np.uint8))
+    assert len(pcs) == 1 and tuple(pcs[0]) == (0, 500, 0, 0)
+
+
+def test_chained_alignment_is_a_valid_global_alignment_and_recovers_the_svs(oracle):
+    windows, contigs, truth = _regions(21, n=3, L=20000)
+    recs = hook.realign_regions_chained(_OracleRunner(oracle), windows, contigs, preset="asm5", bw=2000)
+    for rec, (chrom, start, t), (qn, q), svs in zip(recs, windows, contigs, truth):
+        assert _consumed(rec.cigar) == (len(q), len(t)) and rec.pos == start and rec.reference_end == start + len(t)
+        got = sorted((s.svtype, s.svlen) for s in hook.signatures([rec]))
+        want = sorted((ty, L) for _, ty, L in svs if L >= 30)
+        assert len(got) == len(want)
+        for (gt, gl), (wt, wl) in zip(sorted(got, key=lambda x: x[1]), sorted(want, key=lambda x: x[1])):
+            assert gt == wt and abs(gl - wl) <= 12
+    # re-scoring the stitched CIGAR with the preset gives the reported score
+    p = PRESETS["asm5"]
+    for rec, (_, _, t), (_, q) in zip(recs, windows, contigs):
+        qi = ti = sc = 0
+        qq, tt = hook.encode(q), hook.encode(t)
+        for op, n in rec.cigar:
+            if op == 0:
+                eq = qq[qi:qi + n] == tt[ti:ti + n]
+                sc += int(eq.sum()) * p.a - int((~eq).sum()) * p.b; qi += n; ti += n
+            elif op == 1:
+                sc -= min(p.q + n * p.e, p.q2 + n * p.e2); qi += n
+            else:
+                sc -= min(p.q + n * p.e, p.q2 + n * p.e2); ti += n
+        assert sc == rec.score
+
+
+@pytest.mark.gpu
+def test_gpu_chained_alignment_equals_the_oracle_run(oracle, aligner):
+    windows, contigs, _ = _regions(22, n=4, L=30000)
+    want = hook.realign_regions_chained(_OracleRunner(oracle), windows, contigs, preset="asm5", bw=2000)
+    got = hook.realign_regions_chained(aligner, windows, contigs, preset="asm5", bw=2000)
+    assert got == want
+
+
 def test_library_presets_equal_the_python_table():
     """fsv_preset_lookup is host-only: the library's preset table and ksw_gen_simple_mat restatement against presets.py."""
     from focalsv_b200 import api
