@@ -21,7 +21,7 @@ EXPORTS = ("fsv_init", "fsv_destroy", "fsv_strerror", "fsv_last_error", "fsv_abi
            "fsv_get_stats", "fsv_set_option", "fsv_align_batch", "fsv_batch_create", "fsv_batch_run",
            "fsv_batch_fetch", "fsv_batch_destroy", "fsv_ksw_extz2", "fsv_ksw_extd2", "fsv_task_cells",
            "fsv_lpt_bins", "fsv_measure_int_peak", "fsv_batch_timeline", "fsv_batch_signatures", "fsv_edit_distance_batch",
-           "fsv_preset_lookup", "fsv_realign_regions", "fsv_chain_pieces")
+           "fsv_preset_lookup", "fsv_realign_regions", "fsv_chain_pieces", "fsv_stitch_cigars")
 
 _lib = None
 
@@ -63,6 +63,7 @@ def load_library(path=None):
     lib.fsv_batch_destroy.restype = None
     lib.fsv_chain_pieces.argtypes = [vp, i32, vp, i32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, sz, C.POINTER(sz),
                                      C.POINTER(i32), C.POINTER(i32)]
+    lib.fsv_stitch_cigars.argtypes = [vp, vp, sz, vp, vp, vp, sz, C.POINTER(sz)]
     lib.fsv_preset_lookup.argtypes = [C.c_char_p, C.POINTER(_abi.PresetC), C.POINTER(Scoring)]
     lib.fsv_realign_regions.argtypes = [vp, vp, sz, vp, vp, vp, sz, vp, vp, sz, C.c_char_p, C.c_int, C.c_int, vp, vp, sz, C.POINTER(sz)]
     lib.fsv_task_cells.argtypes = [i32, i32, i32]
@@ -103,6 +104,25 @@ def chain_pieces(query, target, k=19, w=19, max_occ=50, max_gap=100000, min_fill
         if rc != 0:
             raise FsvError(rc, lib.fsv_strerror(rc).decode())
         return out[:n.value], sc.value, na.value
+
+
+def stitch_cigars(pieces, task_of, res, cigar_arena):
+    """fsv_stitch_cigars (host only): one CIGAR (uint32 BAM words) from the pieces of one pair."""
+    lib = load_library()
+    pieces = np.ascontiguousarray(pieces, dtype=_abi.PIECE_DTYPE); task_of = np.ascontiguousarray(task_of, dtype=np.int32)
+    res = np.ascontiguousarray(res, dtype=RESULT_DTYPE); arena = np.ascontiguousarray(cigar_arena, dtype=np.uint32)
+    cap = 256
+    while True:
+        out = np.zeros(cap, dtype=np.uint32)
+        n = C.c_size_t(0)
+        rc = lib.fsv_stitch_cigars(pieces.ctypes.data, task_of.ctypes.data, len(pieces), res.ctypes.data, arena.ctypes.data,
+                                   out.ctypes.data, cap, C.byref(n))
+        if rc == _abi.ERR_CIGAR_CAP:
+            cap = int(n.value) + 16
+            continue
+        if rc != 0:
+            raise FsvError(rc, lib.fsv_strerror(rc).decode())
+        return out[:n.value]
 
 
 def task_cells(qlen, tlen, w):

@@ -125,3 +125,31 @@ extern "C" int fsv_chain_pieces(const uint8_t* query, int32_t qlen, const uint8_
     if (!out.empty()) memcpy(pieces, out.data(), out.size() * sizeof(fsv_piece));
     return FSV_OK;
 }
+
+// Stitch the CIGARs of one pair's pieces (in order) into one: a piece with a task contributes that task's CIGAR, a piece
+// with an empty side a pure gap; neighbouring operations of the same kind are merged (BAM words, len << 4 | op).
+extern "C" int fsv_stitch_cigars(const fsv_piece* pieces, const int32_t* task_of, size_t n_pieces,
+                                 const fsv_result* res, const uint32_t* cigar_arena,
+                                 uint32_t* out, size_t cap, size_t* n_out)
+{
+    if ((!pieces || !task_of) && n_pieces) return FSV_ERR_INVALID;
+    if (!n_out) return FSV_ERR_INVALID;
+    size_t n = 0;
+    auto push = [&](uint32_t op, uint64_t len) {
+        if (!len) return;
+        if (n && n <= cap && (out[n - 1] & 0xfu) == op && (uint64_t)(out[n - 1] >> 4) + len < (1u << 28)) { out[n - 1] += (uint32_t)len << 4; return; }
+        if (n < cap) out[n] = (uint32_t)len << 4 | op;
+        ++n;
+    };
+    for (size_t i = 0; i < n_pieces; ++i) {
+        const int32_t dq = pieces[i].q_end - pieces[i].q_beg, dt = pieces[i].t_end - pieces[i].t_beg;
+        if (task_of[i] >= 0) {
+            if (!res || !cigar_arena) return FSV_ERR_INVALID;
+            const fsv_result& r = res[task_of[i]];
+            for (int32_t k = 0; k < r.n_cigar; ++k) push(cigar_arena[r.cigar_off + k] & 0xfu, cigar_arena[r.cigar_off + k] >> 4);
+        } else if (dq > 0) push(1u, (uint64_t)dq);
+        else if (dt > 0) push(2u, (uint64_t)dt);
+    }
+    *n_out = n;
+    return n > cap ? FSV_ERR_CIGAR_CAP : FSV_OK;
+}

@@ -94,43 +94,29 @@ def realign_regions_chained(aligner, windows, contigs, preset="asm5", bw=2000, m
     t = [encode(s) for _, _, s in windows]
     q_off = np.concatenate([[0], np.cumsum([len(x) for x in q])]).astype(np.int64)
     t_off = np.concatenate([[0], np.cumsum([len(x) for x in t])]).astype(np.int64)
-    plan, rows = [], []
+    per_pair, tasks_l, n_tasks = [], [], 0
     for i in range(len(q)):
         pcs, _, _ = chain_pieces(q[i], t[i], k, w, max_occ, p.bw_long, min_fill)
-        for pc in pcs:
-            dq, dt = int(pc["q_end"] - pc["q_beg"]), int(pc["t_end"] - pc["t_beg"])
-            ti = -1
-            if dq > 0 and dt > 0:
-                ti = len(rows)
-                rows.append((q_off[i] + int(pc["q_beg"]), t_off[i] + int(pc["t_beg"]), dq, dt, abs(dq - dt) + min(ksw_band(bw), 200)))
-            plan.append((i, dq, dt, ti))
-    tasks = np.zeros(len(rows), dtype=_abi.TASK_DTYPE)
-    if rows:
-        r = np.array(rows, dtype=np.int64)
-        tasks["q_off"], tasks["t_off"], tasks["qlen"], tasks["tlen"], tasks["w"] = r[:, 0], r[:, 1], r[:, 2], r[:, 3], r[:, 4]
-    tasks["zdrop"] = -1
+        dq = (pcs["q_end"] - pcs["q_beg"]).astype(np.int64); dt = (pcs["t_end"] - pcs["t_beg"]).astype(np.int64)
+        has = (dq > 0) & (dt > 0)
+        task_of = np.where(has, n_tasks + np.cumsum(has) - 1, -1).astype(np.int32)
+        tk = np.zeros(int(has.sum()), dtype=_abi.TASK_DTYPE)
+        tk["q_off"] = q_off[i] + pcs["q_beg"][has]; tk["t_off"] = t_off[i] + pcs["t_beg"][has]
+        tk["qlen"] = dq[has]; tk["tlen"] = dt[has]
+        tk["w"] = np.abs(dq - dt)[has] + min(ksw_band(bw), 200)
+        tk["zdrop"] = -1                                      # global fills: no z-drop (minimap2's zdrop_inv re-runs are not restated)
+        tasks_l.append(tk); n_tasks += len(tk)
+        per_pair.append((pcs, task_of, dq, dt, has))
+    tasks = np.concatenate(tasks_l) if tasks_l else np.zeros(0, dtype=_abi.TASK_DTYPE)
     res, arena = aligner.align_batch(sc, np.concatenate(q) if q else np.zeros(0, np.uint8),
                                      np.concatenate(t) if t else np.zeros(0, np.uint8), tasks)
-    gap = lambda n: -min(p.q + n * p.e, p.q2 + n * p.e2) if p.q2 >= 0 else -(p.q + n * p.e)      # noqa: E731
-    cig = [[] for _ in q]
-    score = [0] * len(q)
-
-    def push(c, op, n):
-        if n <= 0:
-            return
-        if c and c[-1][0] == op:
-            c[-1] = (op, c[-1][1] + n)
-        else:
-            c.append((op, n))
-    for i, dq, dt, ti in plan:
-        if ti >= 0:
-            for op, n in cigar_tuples(task_cigar(res[ti], arena)):
-                push(cig[i], op, n)
-            score[i] += int(res[ti]["score"])
-        elif dq > 0:
-            push(cig[i], 1, dq); score[i] += gap(dq)
-        elif dt > 0:
-            push(cig[i], 2, dt); score[i] += gap(dt)
+    from .api import stitch_cigars
+    cig, score = [], []
+    for pcs, task_of, dq, dt, has in per_pair:
+        cig.append(cigar_tuples(stitch_cigars(pcs, task_of, res, arena)))
+        gaps = np.where(has, 0, np.maximum(dq, dt))           # pieces with an empty side: one gap of the other side's length
+        gcost = np.minimum(p.q + gaps * p.e, p.q2 + gaps * p.e2) if p.q2 >= 0 else p.q + gaps * p.e
+        score.append(int(res["score"][task_of[has]].astype(np.int64).sum()) - int(gcost[gaps > 0].sum()))
     out = []
     for i, ((chrom, start, _), (qname, _)) in enumerate(zip(windows, contigs)):
         ref_span = sum(n for op, n in cig[i] if op in (0, 2))

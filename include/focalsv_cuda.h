@@ -269,6 +269,13 @@ int fsv_chain_pieces(const uint8_t* query, int32_t qlen, const uint8_t* target, 
                      int k, int w, int max_occ, int max_gap, int min_fill,
                      fsv_piece* pieces, size_t cap, size_t* n_pieces, int32_t* chain_score, int32_t* n_anchors);
 
+/* Stitch the CIGARs of one pair's pieces, in order, into one (host only): task_of[i] = index of piece i's task in `res`
+ * (its CIGAR is copied) or -1 (a piece with an empty side: a pure I / D of the other side's length); neighbouring
+ * operations of the same kind are merged.  FSV_ERR_CIGAR_CAP with *n_out = words needed when `cap` is too small. */
+int fsv_stitch_cigars(const fsv_piece* pieces, const int32_t* task_of, size_t n_pieces,
+                      const fsv_result* res, const uint32_t* cigar_arena,
+                      uint32_t* out, size_t cap, size_t* n_out);
+
 /* ---- roofline denominator ---------------------------------------------
  * Measured issue rate (32-bit lane-ops per second, whole device) of a dependency-free
  * stream of the instruction class the fill kernels are built from:
