@@ -95,8 +95,12 @@ def realign_regions_chained(aligner, windows, contigs, preset="asm5", bw=2000, m
     q_off = np.concatenate([[0], np.cumsum([len(x) for x in q])]).astype(np.int64)
     t_off = np.concatenate([[0], np.cumsum([len(x) for x in t])]).astype(np.int64)
     per_pair, tasks_l, n_tasks = [], [], 0
+    # seeding + chaining is host work per pair and the C call releases the GIL: a few threads, pairs in order
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(16, max(1, len(q)))) as ex:
+        chained = list(ex.map(lambda i: chain_pieces(q[i], t[i], k, w, max_occ, p.bw_long, min_fill)[0], range(len(q))))
     for i in range(len(q)):
-        pcs, _, _ = chain_pieces(q[i], t[i], k, w, max_occ, p.bw_long, min_fill)
+        pcs = chained[i]
         dq = (pcs["q_end"] - pcs["q_beg"]).astype(np.int64); dt = (pcs["t_end"] - pcs["t_beg"]).astype(np.int64)
         has = (dq > 0) & (dt > 0)
         task_of = np.where(has, n_tasks + np.cumsum(has) - 1, -1).astype(np.int32)
