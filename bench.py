@@ -48,6 +48,9 @@ def parse_args():
                          "contig tasks (a=2,b=4,q=4,e=2,w=500,z=400): the one workload whose CPU arm is the reference's OWN "
                          "ksw2_extz2_sse.c compiled in place (cpu_baseline.kind = reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--parity-tasks", type=int, default=40, help="live oracle sample: tasks over the size quantiles (the longest included)")
+    ap.add_argument("--parity-segmented", type=int, default=6, help="live oracle sample: extra segmented tasks (the longest of them always)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--force-exact", action="store_true", help="use only the general int8-exact kernel")
     return ap.parse_args()
@@ -174,18 +177,21 @@ def reference_arm(args, rank, world):
         c, dt, kind = run_cpu(group, idx, cores)
         cells += c; secs += dt
     gcups = cells / secs / 1e9
-    sample = "%d of %d tasks of %s (seed %d), %.3g cells/step" % (len(idx), len(group.tasks), WORKLOAD, CONFIG_SEED, cells / max(args.steps, 1))
+    idx1 = cpu_sample(group, max(args.cpu_seconds / 4, 1.0), 1, 0.45)
+    c1, dt1, _ = run_cpu(group, idx1, 1)
+    sample = "%d of %d tasks of %s (seed %d), %.3g cells/step, handed out largest first" % (len(idx), len(group.tasks), WORKLOAD, CONFIG_SEED, cells / max(args.steps, 1))
     line = {"impl": "reference", "metric": "alignment_gcups", "value": gcups, "unit": "GCUPS", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / max(args.steps, 1) * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
             "regions_per_s": regions * args.steps / secs,
             "config": workload_config(args, world, n_regions),
-            "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": cores, "kind": kind, "sample": sample},
+            "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": cores, "kind": kind, "sample": sample,
+                             "t1_value": c1 / dt1 / 1e9, "t1_sample": "%d tasks (%.3g cells) on one thread" % (len(idx1), c1)},
             "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": ("the reference's own software/hifiasm-0.16.1/ksw2_extz2_sse.c, compiled in place into oracle/_ref "
                      "(gcc -O3 -msse4.1), one task per thread, all host threads") if kind == "reference" else
-                    ("dual-affine ksw_extd2_sse is not in /root/reference (minimap2 2.24 dependency); the CPU arm is the "
-                     "oracle's plain-C restatement (gcc -O3 -msse4.1 + AVX2 clone), one task per thread, all host threads")}
+                    ("port, source-unpinned: dual-affine ksw_extd2_sse is not in /root/reference (minimap2 2.24 dependency); the CPU arm is the "
+                     "oracle's plain-C restatement (gcc -O3 -msse4.1 + AVX2 clone), one task per thread, largest first, all host threads")}
     print(json.dumps(line), flush=True)
 
 
@@ -197,8 +203,9 @@ def workload_config(args, world, n_regions):
                 "sharding": "independent shares per rank, no collective", "world": world,
                 "l2_policy": "inputs+traceback per step exceed the 126 MB L2"}
     return {"workload": "BASELINE configs[1]: FocalSV auto mode, %d SV-rich regions x 2 haplotype contigs per GPU vs "
-                        "hg38-shaped windows, asm5 (a=1,b=19,q=39,e=3,q2=81,e2=1), band 3001, zdrop 200, global + CIGAR"
-                        % args.regions,
+                        "hg38-shaped windows, asm5 (a=1,b=19,q=39,e=3,q2=81,e2=1), band 3001, zdrop 200, global + CIGAR; planted SVs "
+                        "1 per 15 kb with lengths from the chr21 truth set capped at 1.2 kb (band/2 - 300: a longer net offset leaves "
+                        "a band-3001 global task by construction; SURVEY 8d samples up to 12.6 kb)" % args.regions,
             "regions_per_gpu": args.regions, "regions_this_rank": n_regions, "tasks_per_region": 2,
             "seed": CONFIG_SEED, "sharding": "LPT bins by estimated cells, no collective", "world": world,
             "l2_policy": "inputs+traceback per step far exceed the 126 MB L2 (traceback alone is >100 GB/step)"}
@@ -251,6 +258,7 @@ def main():
 
     # ---- device-resident arm: inputs in HBM before the clock starts
     batch = al.batch(group.scoring, group.qarena, group.tarena, group.tasks)
+    batch_plan = batch.plan()
     for _ in range(args.warmup):
         batch.run()
     barrier()
@@ -272,6 +280,16 @@ def main():
     batch.close()
     cells_step = int(res["cells"].sum())
     dev_s = max_over_ranks(dev_ms * 1e-3)         # CUDA events on the launching stream, max over ranks
+    # per-rank view (the job's time is the slowest rank's): device ms per step, cells, segmented tasks / fallbacks
+    mine = [dev_ms / args.steps, float(cells_step), float(st1["segmented_tasks"]), float(st1["segment_fallbacks"]),
+            float((batch_plan & _abi.PLAN_EXCLUSIVE != 0).sum()), float(len(group.tasks))]
+    if world > 1:
+        tt = torch.tensor(mine, dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(tt) for _ in range(world)]
+        dist.all_gather(allr, tt)
+        per_rank = [[float(x) for x in t.tolist()] for t in allr]
+    else:
+        per_rank = [mine]
     wall_s = max_over_ranks(wall)
     tot_cells = sum_over_ranks(float(cells_step)) * args.steps
     tot_regions = sum_over_ranks(float(n_regions)) * args.steps
@@ -279,18 +297,51 @@ def main():
     launches = (st1["fill_launches"] + st1["backtrack_launches"] + st1["other_launches"]
                 - st0["fill_launches"] - st0["backtrack_launches"] - st0["other_launches"])
 
-    # ---- parity spot check of what was just timed (oracle as checker only)
+    # ---- parity gate on what was just timed (oracle as checker only).  (1) When this is the default N=1 workload, EVERY
+    # task is compared with the committed oracle digests (tests/golden/parity_cfg2_g0.npz, made by scripts/parity_full.py
+    # oracle cfg2).  (2) Always: a live oracle run in this process on a sample stratified over the size quantiles that
+    # includes the longest task, segmented tasks (the cold-start + stitch path) and exclusive-launch tasks.
     parity = None
-    if rank == 0:
+    plan = batch_plan
+    seg_mask = (plan & _abi.PLAN_SEGMENTED) != 0
+    if rank == 0 and not args.no_parity:
         from oracle import oracle as O
-        small = np.argsort(group.tasks["qlen"].astype(np.int64) + group.tasks["tlen"])[:4]
-        ores, oarena = O.run_batch(group.scoring, group.qarena, group.tarena, group.tasks[small], threads=4)
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import parity_full as PF
+        parity = {"bit_exact": True}
+        dpath = PF.path_of(WORKLOAD, 0)
+        if world == 1 and args.regions == (5000 if WORKLOAD == "cfg2" else -1) and os.path.exists(dpath):
+            z = np.load(dpath)
+            d, h = PF.digest(group.tasks, res, cig)
+            nf = len(PF.FIELDS)
+            same_work = z["digest"].shape == d.shape and np.array_equal(z["digest"][:, nf:], d[:, nf:])
+            n_bad = int(((z["digest"][:, :nf] != d[:, :nf]).any(axis=1) | (z["cigar_hash"] != h)).sum()) if same_work else -1
+            parity["all_tasks"] = {"tasks_checked": int(len(d)) if same_work else 0, "mismatches": n_bad,
+                                   "against": "tests/golden/parity_%s_g0.npz (oracle digests of every task: 11 ksw_extz_t fields, cells, CIGAR hash)" % WORKLOAD}
+            parity["bit_exact"] &= same_work and n_bad == 0
+        n_diag = group.tasks["qlen"].astype(np.int64) + group.tasks["tlen"] - 1
+        order = np.argsort(n_diag, kind="stable")
+        rng = np.random.default_rng(7)
+        pick = set(order[np.linspace(0, len(order) - 1, args.parity_tasks).astype(np.int64)].tolist())      # size quantiles, longest included
+        segs = np.flatnonzero(seg_mask)
+        if len(segs):
+            pick.add(int(segs[np.argmax(n_diag[segs])]))
+            pick.update(int(x) for x in rng.choice(segs, min(args.parity_segmented, len(segs)), replace=False))
+        excl = np.flatnonzero((plan & _abi.PLAN_EXCLUSIVE) != 0)
+        pick.update(int(x) for x in excl[:2])
+        pick = np.array(sorted(pick), dtype=np.int64)
+        t0 = time.perf_counter()
+        ores, oarena = O.run_batch(group.scoring, group.qarena, group.tarena, group.tasks[pick], threads=os.cpu_count() or 1)
         ok = True
-        for k, i in enumerate(small):
+        for k, i in enumerate(pick):
             gc = api.task_cigar(res[i], cig)
             oc = oarena[int(ores[k]["cigar_off"]):int(ores[k]["cigar_off"]) + int(ores[k]["n_cigar"])]
-            ok &= all(int(res[i][f]) == int(ores[k][f]) for f in _abi.EZ_FIELDS) and np.array_equal(gc, oc)
-        parity = {"tasks_checked": int(len(small)), "bit_exact": bool(ok)}
+            ok &= all(int(res[i][f]) == int(ores[k][f]) for f in _abi.EZ_FIELDS) and np.array_equal(gc, oc) and int(res[i]["cells"]) == int(ores[k]["cells"])
+        parity["live_sample"] = {"tasks_checked": int(len(pick)), "bit_exact": bool(ok), "longest_antidiagonals": int(n_diag[pick].max()),
+                                 "segmented_in_sample": int(seg_mask[pick].sum()), "exclusive_in_sample": int(((plan[pick] & _abi.PLAN_EXCLUSIVE) != 0).sum()),
+                                 "oracle_seconds": time.perf_counter() - t0}
+        parity["bit_exact"] = bool(parity["bit_exact"] and ok)
+        parity["tasks_checked"] = int(max(len(pick), parity.get("all_tasks", {}).get("tasks_checked", 0)))
 
     # ---- end-to-end arm: host buffers through the public API, H2D and D2H inside the clock
     e2e = None
@@ -359,9 +410,12 @@ def main():
         cores = os.cpu_count() or 1
         idx = cpu_sample(group, args.cpu_seconds, cores, 0.45)
         c, dt, knd = run_cpu(group, idx, cores)
+        idx1 = cpu_sample(group, max(args.cpu_seconds / 4, 1.0), 1, 0.45)
+        c1, dt1, _ = run_cpu(group, idx1, 1)
         cpu_baseline = {"value": c / dt / 1e9, "unit": "GCUPS", "cores": cores, "kind": knd,
-                        "sample": "%d of %d tasks (%.3g cells) of the same workload, one task per thread" % (len(idx), len(group.tasks), c),
-                        "seconds": dt}
+                        "sample": "%d of %d tasks (%.3g cells) of the same workload, largest first, one task per thread" % (len(idx), len(group.tasks), c),
+                        "seconds": dt, "t1_value": c1 / dt1 / 1e9, "t1_sample": "%d tasks (%.3g cells) on one thread" % (len(idx1), c1),
+                        "note": "port = the oracle's plain-C restatement (dual-affine source unpinned: minimap2 2.24 is not in the reference tree)" if knd == "port" else "the reference's own ksw2_extz2_sse.c compiled in place"}
 
     if rank == 0:
         line = {"metric": "alignment_gcups", "value": gcups, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
@@ -371,11 +425,18 @@ def main():
                 "config": workload_config(args, world, n_regions), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "parity": parity, "exact_path_tasks": int(st1["exact_path_tasks"] - st0["exact_path_tasks"]) // max(args.steps, 1),
+                "segmented_tasks": int(st1["segmented_tasks"]), "segment_fallbacks": int(st1["segment_fallbacks"]),
+                "exclusive_tasks": int((batch_plan & _abi.PLAN_EXCLUSIVE != 0).sum()),
+                "per_rank": {"fields": ["device_ms_per_step", "cells_per_step", "segmented_tasks", "segment_fallbacks", "exclusive_tasks", "tasks"],
+                             "values": per_rank},
                 "timing": "sum over steps of CUDA-event time on the library's launch stream, max over ranks"}
         print(json.dumps(line), flush=True)
     al.close()
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0 and parity is not None and not parity["bit_exact"]:
+        sys.stderr.write("bench.py: PARITY FAILED: %s\n" % json.dumps(parity))
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -1,4 +1,4 @@
-"""ctypes / numpy mirrors of include/focalsv_cuda.h (ABI version 3).
+"""ctypes / numpy mirrors of include/focalsv_cuda.h (ABI version 4).
 
 Kept in one place so that the product binding (focalsv_b200.api), the oracle
 wrapper (oracle/oracle.py) and the tests all see the same layouts.
@@ -7,7 +7,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 NEG_INF = -0x40000000
 
 # ksw2.h:8-14
@@ -18,6 +18,8 @@ EZ_APPROX_MAX = 0x08
 EZ_APPROX_DROP = 0x10
 EZ_EXTZ_ONLY = 0x40
 EZ_REV_CIGAR = 0x80
+
+PLAN_DPX, PLAN_GENERAL, PLAN_SEGMENTED, PLAN_EXCLUSIVE = 1, 2, 4, 8
 
 OK = 0
 ERR_NO_DEVICE = -1

@@ -21,7 +21,7 @@ EXPORTS = ("fsv_init", "fsv_destroy", "fsv_strerror", "fsv_last_error", "fsv_abi
            "fsv_get_stats", "fsv_set_option", "fsv_align_batch", "fsv_batch_create", "fsv_batch_run",
            "fsv_batch_fetch", "fsv_batch_destroy", "fsv_ksw_extz2", "fsv_ksw_extd2", "fsv_task_cells",
            "fsv_lpt_bins", "fsv_measure_int_peak", "fsv_batch_timeline", "fsv_batch_signatures", "fsv_edit_distance_batch",
-           "fsv_preset_lookup", "fsv_realign_regions", "fsv_chain_pieces", "fsv_stitch_cigars")
+           "fsv_preset_lookup", "fsv_realign_regions", "fsv_chain_pieces", "fsv_stitch_cigars", "fsv_batch_plan")
 
 _lib = None
 
@@ -58,6 +58,12 @@ def load_library(path=None):
     lib.fsv_batch_fetch.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
     lib.fsv_batch_destroy.argtypes = [vp]
     lib.fsv_batch_timeline.argtypes = [vp, vp]
+    lib.fsv_batch_plan.argtypes = [vp, vp]
+    i8p = C.POINTER(C.c_int8)
+    lib.fsv_ksw_extz2.argtypes = [vp, C.c_int, vp, C.c_int, vp, C.c_int8, i8p, C.c_int8, C.c_int8, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  vp, vp, C.c_int]
+    lib.fsv_ksw_extd2.argtypes = [vp, C.c_int, vp, C.c_int, vp, C.c_int8, i8p, C.c_int8, C.c_int8, C.c_int8, C.c_int8, C.c_int, C.c_int,
+                                  C.c_int, C.c_int, vp, vp, C.c_int]
     lib.fsv_batch_signatures.argtypes = [vp, vp, C.c_int, vp, sz, C.POINTER(sz)]
     lib.fsv_edit_distance_batch.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp]
     lib.fsv_batch_destroy.restype = None
@@ -348,7 +354,14 @@ class Batch(object):
         self._al._check(self._lib.fsv_batch_timeline(self._h, out.ctypes.data), "fsv_batch_timeline")
         return out
 
+    def plan(self):
+        """Per task: _abi.PLAN_* bits (kernel family, segmented, exclusive launch), warps in bits 8..11, segments in bits 16.. ."""
+        out = np.zeros(max(len(self.tasks), 1), dtype=np.int32)
+        self._al._check(self._lib.fsv_batch_plan(self._h, out.ctypes.data), "fsv_batch_plan")
+        return out[:len(self.tasks)]
+
     def close(self):
+        # (a batch that outlives its Aligner was detached by fsv_destroy: destroying it only frees the host object)
         if getattr(self, "_h", None):
             self._lib.fsv_batch_destroy(self._h)
             self._h = None

@@ -41,9 +41,33 @@ def _units(defs):
     return [(n, s, f + list(defs)) for n, s, f in units]
 
 
+def _deps(src):
+    """Files a translation unit is rebuilt for: itself, the headers it includes (recursively, csrc/ and include/ only)."""
+    seen, todo = set(), [src]
+    while todo:
+        f = todo.pop()
+        if f in seen or not os.path.exists(f):
+            continue
+        seen.add(f)
+        for ln in open(f, errors="replace"):
+            ln = ln.strip()
+            if ln.startswith("#include \""):
+                inc = ln.split('"')[1]
+                todo.append(os.path.normpath(os.path.join(os.path.dirname(f), inc)))
+    return seen | {os.path.abspath(__file__)}
+
+
 def _compile(objdir, name, src, flags):
     obj = os.path.join(objdir, name + ".o")
+    stamp = obj + ".flags"
+    want = " ".join(CFLAGS + flags)
+    if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == want and \
+            all(os.path.getmtime(d) <= os.path.getmtime(obj) for d in _deps(src)):
+        return name, obj, 0, "(up to date)\n"
     r = subprocess.run([NVCC] + CFLAGS + flags + ["-c", "-o", obj, src], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode == 0:
+        with open(stamp, "w") as fh:
+            fh.write(want)
     return name, obj, r.returncode, r.stdout
 
 

@@ -75,6 +75,7 @@ struct fsv_ctx {
     // device blocks of destroyed batches, kept for the next one (cudaMalloc / cudaFree of GB-sized blocks
     // cost tens of milliseconds per call and synchronise the device)
     std::vector<std::pair<void*, size_t>> dcache;
+    std::vector<struct fsv_batch*> live;      // batches created on this context and not destroyed yet (fsv_destroy detaches them)
 };
 
 static void* dev_alloc(fsv_ctx* c, size_t bytes, size_t* got)
@@ -148,6 +149,7 @@ struct fsv_batch {
     long long* d_timeline = nullptr;
     size_t sz_q = 0, sz_t = 0, sz_tasks = 0, sz_work = 0, sz_results = 0, sz_ctrl = 0, sz_cursor = 0, sz_cigar = 0, sz_timeline = 0;
     int state = 0;                    // 0 created, 1 run
+    std::vector<uint8_t> is_seg, is_excl;   // per task: cut into segments / runs on the exclusive launch (fsv_batch_plan)
     // segmented tasks
     std::vector<DevSeg> segs;
     std::vector<SegTask> seg_tasks;
@@ -217,10 +219,15 @@ extern "C" int fsv_init(int device, fsv_ctx** out)
     return FSV_OK;
 }
 
+static void free_batch_device(fsv_batch* b);
 extern "C" void fsv_destroy(fsv_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
+    // batches that outlive their context are detached: their device blocks go back now, fsv_batch_destroy only
+    // deletes the host object, every other call on them returns FSV_ERR_STATE
+    for (fsv_batch* b : c->live) { free_batch_device(b); b->ctx = nullptr; b->state = -1; }
+    c->live.clear();
     if (c->d_pool) cudaFree(c->d_pool);
     if (c->d_ws) cudaFree(c->d_ws);
     if (c->d_tables) cudaFree(c->d_tables);
@@ -367,8 +374,12 @@ static void free_batch_device(fsv_batch* b)
 extern "C" void fsv_batch_destroy(fsv_batch* b)
 {
     if (!b) return;
-    cudaSetDevice(b->ctx->device);
-    free_batch_device(b);
+    if (b->ctx) {
+        cudaSetDevice(b->ctx->device);
+        free_batch_device(b);
+        auto& lv = b->ctx->live;
+        lv.erase(std::remove(lv.begin(), lv.end(), b), lv.end());
+    }
     delete b;
 }
 
@@ -742,6 +753,8 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
     tr.lap("create: H2D");
 #undef CKB
     c->stats.h2d_bytes += (int64_t)(qbytes + tbytes + n * (sizeof(DevTask) + 4));
+    b->is_seg.swap(is_seg); b->is_excl.swap(is_excl);
+    c->live.push_back(b);
     *out = b;
     return FSV_OK;
 }
@@ -760,6 +773,7 @@ extern "C" int fsv_batch_run(fsv_batch* b)
 {
     if (!b) return FSV_ERR_INVALID;
     fsv_ctx* c = b->ctx;
+    if (!c) return FSV_ERR_STATE;             // its context was destroyed
     HostTrace tr;
     CK(c, cudaSetDevice(c->device));
     // ---- scratch: page pool, free stack, page tables, general-kernel windows
@@ -822,9 +836,14 @@ extern "C" int fsv_batch_run(fsv_batch* b)
     R.segs = b->d_segs; R.seg_tasks = b->d_seg_tasks; R.seg_rec = b->d_seg_rec; R.seg_snap = b->d_seg_snap;
     R.seg_tables = b->d_seg_tables; R.seg_done = b->d_seg_done; R.seg_cancel = b->d_seg_done + b->seg_tasks.size(); R.seg_released = b->d_seg_done + 2 * b->seg_tasks.size(); R.seg_foot = b->d_seg_foot;
 
-    cudaEvent_t e0, e1;
+    // events of this run, destroyed on every way out
+    struct Events {
+        cudaEvent_t e0 = nullptr, e1 = nullptr; std::vector<cudaEvent_t> done;
+        ~Events() { for (auto e : done) if (e) cudaEventDestroy(e); if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+    } ev;
+    ev.done.assign(b->launches.size() + b->seg_launches.size(), nullptr);
+    cudaEvent_t& e0 = ev.e0; cudaEvent_t& e1 = ev.e1; std::vector<cudaEvent_t>& done = ev.done;
     CK(c, cudaEventCreate(&e0)); CK(c, cudaEventCreate(&e1));
-    std::vector<cudaEvent_t> done(b->launches.size() + b->seg_launches.size());
     CK(c, cudaEventRecord(e0, c->stream));
     // every kernel variant runs concurrently on its own stream; they share the page pool, so the long
     // tasks of one class overlap the short tasks of all the others
@@ -883,8 +902,6 @@ extern "C" int fsv_batch_run(fsv_batch* b)
     tr.lap("run: kernels");
     float ms = 0;
     CK(c, cudaEventElapsedTime(&ms, e0, e1));
-    for (auto e : done) cudaEventDestroy(e);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     c->stats.total_ms = ms; c->stats.fill_ms = ms; c->stats.backtrack_ms = 0;   // the CIGAR walk runs inside the fill kernels
     c->stats.traceback_bytes = b->tb_bytes_total;
     c->stats.segmented_tasks = (int64_t)b->seg_tasks.size();
@@ -906,7 +923,7 @@ extern "C" int fsv_batch_fetch(fsv_batch* b, fsv_result* out, uint32_t* cigar, s
 {
     if (!b || (!out && b->n)) return FSV_ERR_INVALID;
     fsv_ctx* c = b->ctx;
-    if (b->state != 1) return FSV_ERR_STATE;
+    if (!c || b->state != 1) return FSV_ERR_STATE;
     CK(c, cudaSetDevice(c->device));
     int64_t used = 0;
     if (b->n) CK(c, cudaMemcpyAsync(out, b->d_results, b->n * sizeof(fsv_result), cudaMemcpyDeviceToHost, c->stream));
@@ -1003,7 +1020,7 @@ extern "C" int fsv_batch_signatures(fsv_batch* b, const int64_t* ref_start, int 
 {
     if (!b || !n_out || (cap && !out)) return FSV_ERR_INVALID;
     fsv_ctx* c = b->ctx;
-    if (b->state != 1) return FSV_ERR_STATE;
+    if (!c || b->state != 1) return FSV_ERR_STATE;
     *n_out = 0;
     const int n = (int)b->n;
     if (!n) return FSV_OK;
@@ -1053,9 +1070,23 @@ extern "C" int fsv_batch_timeline(fsv_batch* b, int64_t* start_end_ns)
 {
     if (!b || !start_end_ns) return FSV_ERR_INVALID;
     fsv_ctx* c = b->ctx;
-    if (b->state != 1) return FSV_ERR_STATE;
+    if (!c || b->state != 1) return FSV_ERR_STATE;
     CK(c, cudaSetDevice(c->device));
     if (b->n) CK(c, cudaMemcpy(start_end_ns, b->d_timeline, b->n * 16, cudaMemcpyDeviceToHost));
+    return FSV_OK;
+}
+
+extern "C" int fsv_batch_plan(const fsv_batch* b, int32_t* plan)
+{
+    if (!b || (!plan && b->n)) return FSV_ERR_INVALID;
+    for (size_t i = 0; i < b->n; ++i) {
+        int32_t v = 0;
+        if (b->tasks[i].kind == 1) v |= b->is_dpx[i] ? FSV_PLAN_DPX : FSV_PLAN_GENERAL;
+        if (i < b->is_seg.size() && b->is_seg[i]) v |= FSV_PLAN_SEGMENTED | ((int32_t)b->seg_tasks[(size_t)b->tasks[i].seg_id].n_segs << 16);
+        if (i < b->is_excl.size() && b->is_excl[i]) v |= FSV_PLAN_EXCLUSIVE;
+        v |= (b->tasks[i].nw & 0xf) << 8;
+        plan[i] = v;
+    }
     return FSV_OK;
 }
 
@@ -1174,7 +1205,7 @@ extern "C" int fsv_realign_regions(fsv_ctx* c, const uint8_t* ref_codes, size_t 
         fsv_record& r = out[i];
         r.pos = region_start[i]; r.ref_end = region_start[i];
         r.cigar_off = res[i].cigar_off; r.n_cigar = res[i].n_cigar; r.query_length = contig_len[i];
-        r.score = res[i].score; r.zdropped = res[i].zdropped; r.is_reverse = 0; r.mapq = 60;
+        r.score = res[i].score; r.zdropped = res[i].zdropped; r.is_reverse = 0; r.mapq = res[i].zdropped ? 0 : 60;      // a dropped task stops at its maximum cell: not a full-length alignment
         if (rc == FSV_OK)
             for (int32_t k = 0; k < r.n_cigar; ++k) {
                 const uint32_t wd = cigar[r.cigar_off + k];

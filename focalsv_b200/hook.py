@@ -71,6 +71,9 @@ def realign_regions_abi(aligner, ref_codes, regions, contigs, preset="asm5", bw=
     out = []
     for r, (chrom, _, _), (qname, _) in zip(rec, regions, contigs):
         cig = cigar_tuples(arena[int(r["cigar_off"]):int(r["cigar_off"]) + int(r["n_cigar"])])
+        q_used = sum(n for op, n in cig if op in (0, 1, 4))
+        if q_used < int(r["query_length"]):                   # z-dropped: soft clip for the unaligned tail (see records_from_results)
+            cig = cig + [(4, int(r["query_length"]) - q_used)]
         out.append(AlignedContig(qname, chrom, int(r["pos"]), int(r["ref_end"]), cig, bool(r["is_reverse"]), int(r["mapq"]),
                                  int(r["query_length"]), int(r["score"]), bool(r["zdropped"])))
     return out
@@ -87,6 +90,8 @@ def realign_regions_chained(aligner, windows, contigs, preset="asm5", bw=2000, m
     `aligner` is anything with align_batch(sc, qarena, tarena, tasks) -> (results, cigar_arena).  The result is a valid
     global alignment of each pair; it equals minimap2's only as far as the restated seeding does (parity unpinned)."""
     from .api import chain_pieces
+    if preset not in SEEDING:
+        raise ValueError("realign_regions_chained: preset %r has no seeding parameters (minimap2 presets only: %s)" % (preset, ", ".join(sorted(SEEDING))))
     p = PRESETS[preset]
     sc = scoring_for(preset)
     k, w = SEEDING[preset]
@@ -115,6 +120,11 @@ def realign_regions_chained(aligner, windows, contigs, preset="asm5", bw=2000, m
     res, arena = aligner.align_batch(sc, np.concatenate(q) if q else np.zeros(0, np.uint8),
                                      np.concatenate(t) if t else np.zeros(0, np.uint8), tasks)
     from .api import stitch_cigars
+    if len(res) and (res["status"] != 0).any():
+        raise ValueError("realign_regions_chained: %d piece tasks were reset (scoring outside ksw2's int8 range)" % int((res["status"] != 0).sum()))
+    if len(res) and (res["zdropped"] != 0).any():
+        # global fills run without z-drop; a piece can still stop early when |dq - dt| exceeds its band (ksw2_extz2_sse.c:111-114)
+        raise ValueError("realign_regions_chained: %d pieces ran out of band" % int((res["zdropped"] != 0).sum()))
     cig, score = [], []
     for pcs, task_of, dq, dt, has in per_pair:
         cig.append(cigar_tuples(stitch_cigars(pcs, task_of, res, arena)))
@@ -129,12 +139,24 @@ def realign_regions_chained(aligner, windows, contigs, preset="asm5", bw=2000, m
 
 
 def records_from_results(windows, contigs, res, arena):
+    """AlignedContig records of one global task per pair.  A task that ksw2 z-dropped (or whose band ran out) stops at its
+    maximum cell: its CIGAR consumes only a prefix of the contig.  Such a record gets a trailing soft clip for the
+    unaligned tail (so that the query-consuming operations add up to query_length, as every SAM record must), mapq 0 and
+    zdropped = True: minimap2 would split or re-run that alignment (row f2), consumers must not take it for a full one."""
     out = []
     for i, ((chrom, start, _), (qname, qseq)) in enumerate(zip(windows, contigs)):
+        if int(res[i]["status"]) != 0:
+            raise ValueError("pair %d (%s): task status %d (scoring outside ksw2's int8 range)" % (i, qname, int(res[i]["status"])))
         cig = cigar_tuples(task_cigar(res[i], arena))
         ref_span = sum(n for op, n in cig if op in (0, 2))
-        out.append(AlignedContig(qname, chrom, int(start), int(start) + ref_span, cig, False, 60, len(qseq),
-                                 int(res[i]["score"]), bool(res[i]["zdropped"])))
+        q_used = sum(n for op, n in cig if op in (0, 1, 4))
+        dropped = bool(res[i]["zdropped"])
+        mapq = 60
+        if q_used < len(qseq):
+            cig = cig + [(4, len(qseq) - q_used)]
+            mapq = 0
+        out.append(AlignedContig(qname, chrom, int(start), int(start) + ref_span, cig, False, mapq, len(qseq),
+                                 int(res[i]["score"]), dropped))
     return out
 
 

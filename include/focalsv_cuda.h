@@ -16,7 +16,13 @@
  *   software/hifiasm-0.16.1/ksw2.h:54-55   ksw_extz2_sse(...)   -> fsv_ksw_extz2 / fsv_align_batch (q2<0)
  *   software/hifiasm-0.16.1/ksw2.h:60-61   ksw_extd2_sse(...)   -> fsv_ksw_extd2 / fsv_align_batch
  * Results (every fsv_result field and every CIGAR word) are bit-identical to
- * those functions, including their band-rounding and tie-break behaviour.
+ * ksw_extz2_sse, including its band-rounding and tie-break behaviour: PINNED against the reference's own file compiled
+ * in place (oracle/_ref, tests/test_oracle_vs_ref.py, tests/golden/kat_extz2.npz).
+ * ksw_extd2_sse: the reference tree holds only its PROTOTYPE (ksw2.h:60-61); the body is minimap2 2.24's
+ * ksw2_extd2_sse.c, a dependency that is absent from /root/reference and from this image.  The dual-affine results are
+ * bit-identical to this repository's restatement of that published algorithm (oracle/ksw2_oracle.c, fsvo_extd2), which is
+ * anchored (extd2(q,e,q,e) == extz2(q,e) on every field; global score == an independent two-piece Gotoh DP; every
+ * CIGAR re-scores to ez.score) but PARITY-UNPINNED at the source level.
  *
  * There is NO CPU fallback behind this ABI: without a CUDA device fsv_init
  * fails with FSV_ERR_NO_DEVICE.
@@ -31,7 +37,7 @@
 extern "C" {
 #endif
 
-#define FSV_ABI_VERSION 3
+#define FSV_ABI_VERSION 4
 
 /* ksw2.h:6 */
 #define FSV_NEG_INF (-0x40000000)
@@ -171,6 +177,13 @@ void fsv_batch_destroy(fsv_batch* batch);
 /* Per-task device timeline of the last run (GPU globaltimer, ns): start_end_ns[2*i] = when task i got its
  * traceback pages and started, [2*i+1] = when its CIGAR was written.  For schedule analysis / tracing. */
 int fsv_batch_timeline(fsv_batch* batch, int64_t* start_end_ns);
+/* How the batch was planned (host only, valid after fsv_batch_create): plan[i] = FSV_PLAN_* bits of task i,
+ * warps per task in bits 8..11, number of segments in bits 16..  For parity sampling and schedule analysis. */
+#define FSV_PLAN_DPX       0x1   /* runs on the DPX fill kernel */
+#define FSV_PLAN_GENERAL   0x2   /* runs on the general int8-exact kernel */
+#define FSV_PLAN_SEGMENTED 0x4   /* cut into segments that run on separate CTAs */
+#define FSV_PLAN_EXCLUSIVE 0x8   /* runs on the exclusive (one CTA per SM) launch */
+int fsv_batch_plan(const fsv_batch* batch, int32_t* plan);
 
 /* ---- Level 1: the pipeline hook -------------------------------
  * What FocalSV does around its `minimap2 -a -x <preset> --cs -r2k ref.fa contigs.fa` call
@@ -203,7 +216,8 @@ typedef struct fsv_record {
     int32_t score;
     int32_t zdropped;
     int32_t is_reverse;       /* always 0: strand selection belongs to seeding (row f2) */
-    int32_t mapq;             /* placeholder 60, as a unique full-length contig alignment gets */
+    int32_t mapq;             /* placeholder: 60, as a unique full-length contig alignment gets; 0 when zdropped (the CIGAR
+                               * then ends at the maximum cell and consumes only a prefix of the contig) */
 } fsv_record;
 int fsv_realign_regions(fsv_ctx* ctx, const uint8_t* ref_codes, size_t ref_len,
                         const int64_t* region_start, const int64_t* region_end,

@@ -30,7 +30,7 @@ def build(verbose=False):
     os.makedirs(OUT, exist_ok=True)
     built = {}
     port = os.path.join(OUT, "libfsv_oracle.so")
-    srcs = [os.path.join(HERE, "ksw2_oracle.c"), os.path.join(HERE, "ksw2_oracle.h"),
+    srcs = [os.path.join(HERE, "ksw2_oracle.c"), os.path.join(HERE, "ksw2_oracle.h"), os.path.join(HERE, "batch_pool.h"),
             os.path.join(HERE, "..", "include", "focalsv_cuda.h")]
     if _stale(port, srcs):
         cmd = ["gcc"] + CFLAGS + ["-o", port, srcs[0]]
@@ -42,7 +42,7 @@ def build(verbose=False):
     ref_src = os.path.join(REF_DIR, "ksw2_extz2_sse.c")
     if os.path.exists(ref_src):
         shim = os.path.join(HERE, "ref_shim.c")
-        if _stale(ref, [shim, ref_src, os.path.join(REF_DIR, "ksw2.h")]):
+        if _stale(ref, [shim, ref_src, os.path.join(REF_DIR, "ksw2.h"), os.path.join(HERE, "batch_pool.h")]):
             cmd = ["gcc"] + CFLAGS + ["-I", REF_DIR, "-o", ref, shim, ref_src]
             if verbose:
                 print(" ".join(cmd))

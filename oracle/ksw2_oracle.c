@@ -680,55 +680,22 @@ int32_t fsvo_score_cigar(int qlen, const uint8_t* query, int tlen, const uint8_t
 }
 
 /* ====================================================================== */
-/* thread-pool batch driver (bench.py cpu_baseline, kind "port")           */
-#include <pthread.h>
-typedef struct {
-    const fsv_scoring* sc; const uint8_t *qa, *ta; const fsv_task* tasks; int64_t n;
-    fsv_result* out; uint32_t** cig; int64_t next; pthread_mutex_t mu;
-} pool_t;
-
-static void* pool_worker(void* arg)
+/* thread-pool batch driver (bench.py cpu_baseline, kind "port"; parity scripts): batch_pool.h */
+#include "batch_pool.h"
+static void oracle_run_one(const fsv_scoring* sc, const uint8_t* qa, const uint8_t* ta, const fsv_task* t,
+                           fsv_result* out, uint32_t* cig, int cap)
 {
-    pool_t* p = (pool_t*)arg;
-    for (;;) {
-        int64_t i; const fsv_task* t; int cap;
-        pthread_mutex_lock(&p->mu); i = p->next++; pthread_mutex_unlock(&p->mu);
-        if (i >= p->n) break;
-        t = &p->tasks[i];
-        cap = t->qlen + t->tlen + 2;
-        p->cig[i] = (t->flag & FSV_EZ_SCORE_ONLY) ? 0 : (uint32_t*)malloc((size_t)cap * 4);
-        if (p->sc->q2 < 0)
-            fsvo_extz2(t->qlen, p->qa + t->q_off, t->tlen, p->ta + t->t_off, p->sc->m, p->sc->mat, p->sc->q, p->sc->e,
-                       t->w, t->zdrop, t->end_bonus, t->flag, &p->out[i], p->cig[i], cap, 0);
-        else
-            fsvo_extd2(t->qlen, p->qa + t->q_off, t->tlen, p->ta + t->t_off, p->sc->m, p->sc->mat, p->sc->q, p->sc->e,
-                       p->sc->q2, p->sc->e2, t->w, t->zdrop, t->end_bonus, t->flag, &p->out[i], p->cig[i], cap, 0);
-    }
-    return 0;
+    if (sc->q2 < 0)
+        fsvo_extz2(t->qlen, qa + t->q_off, t->tlen, ta + t->t_off, sc->m, sc->mat, sc->q, sc->e,
+                   t->w, t->zdrop, t->end_bonus, t->flag, out, cig, cap, 0);
+    else
+        fsvo_extd2(t->qlen, qa + t->q_off, t->tlen, ta + t->t_off, sc->m, sc->mat, sc->q, sc->e,
+                   sc->q2, sc->e2, t->w, t->zdrop, t->end_bonus, t->flag, out, cig, cap, 0);
 }
 
 int fsvo_run_batch(const fsv_scoring* sc, const uint8_t* qarena, const uint8_t* tarena,
                    const fsv_task* tasks, int64_t n, int threads, fsv_result* out,
                    uint32_t* cigar_arena, int64_t cigar_cap, int64_t* cigar_used)
 {
-    pool_t p; pthread_t* th; int i; int64_t k, used = 0;
-    if (threads < 1) threads = 1;
-    p.sc = sc; p.qa = qarena; p.ta = tarena; p.tasks = tasks; p.n = n; p.out = out; p.next = 0;
-    p.cig = (uint32_t**)calloc((size_t)n + 1, sizeof(uint32_t*));
-    pthread_mutex_init(&p.mu, 0);
-    th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)threads);
-    for (i = 0; i < threads; ++i) pthread_create(&th[i], 0, pool_worker, &p);
-    for (i = 0; i < threads; ++i) pthread_join(th[i], 0);
-    for (k = 0; k < n; ++k) {
-        out[k].cigar_off = used;
-        if (p.cig[k]) {
-            if (cigar_arena && used + out[k].n_cigar <= cigar_cap)
-                memcpy(cigar_arena + used, p.cig[k], (size_t)out[k].n_cigar * 4);
-            free(p.cig[k]);
-        }
-        used += out[k].n_cigar;
-    }
-    if (cigar_used) *cigar_used = used;
-    free(th); free(p.cig); pthread_mutex_destroy(&p.mu);
-    return 0;
+    return bp_run_batch(oracle_run_one, sc, qarena, tarena, tasks, n, threads, out, cigar_arena, cigar_cap, cigar_used);
 }
