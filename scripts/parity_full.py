@@ -50,9 +50,10 @@ def groups_of(cfg):
         from focalsv_b200.presets import PRESETS, ksw_band
         rng = np.random.default_rng(4242)
         pairs = []
-        for _ in range(2):
+        for k in range(2):
             ref = synth.random_seq(rng, 1000000)
-            q, _ = synth.plant_svs(rng, ref, 60, max_net=1200, max_len=1000)
+            # task 0: a few small SVs, the alignment runs to the end; task 1: many large ones, ksw2's z-drop ends it inside a later segment
+            q, _ = synth.plant_svs(rng, ref, 60, max_net=1200, max_len=1000) if k else synth.plant_svs(rng, ref, 12, max_net=300, max_len=150)
             pairs.append((synth.mutate(rng, q, 0.003, 0.001, 0.001), ref))
         p = PRESETS["asm10"]
         return [synth._pack("long1m.asm10", "asm10", pairs, ksw_band(p.bw), p.zdrop, flags=np.array([0, _abi.EZ_EXTZ_ONLY], dtype=np.int32))]

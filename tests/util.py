@@ -83,3 +83,13 @@ def compare_group(O, al, group, threads=8):
         if not same_result(ores[i], ocigs[i], gres[i], gc) or int(ores[i]["cells"]) != int(gres[i]["cells"]):
             bad.append(i)
     return bad, ores, gres
+
+
+class OracleRunner(object):
+    """align_batch on the CPU oracle: lets host-side code that takes "anything with align_batch" (hook.realign_regions,
+    hook.realign_regions_chained, dropin.align_fastas) be exercised without a GPU.  Test infrastructure."""
+    def __init__(self, O, threads=8):
+        self.O, self.threads = O, threads
+
+    def align_batch(self, sc, qa, ta, tasks):
+        return self.O.run_batch(sc, qa, ta, tasks, threads=self.threads)
