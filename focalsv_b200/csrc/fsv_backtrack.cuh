@@ -8,11 +8,11 @@
 // B200 shape: the walk runs in the fill kernel's own CTA right after the last
 // antidiagonal (the rows it reads first are the ones written last, still in L2), on
 // ONE warp.  It is a pointer chase, so instead of one dependent load per step the
-// 32 lanes speculatively fetch the next 32 cells along the direction the current
-// state moves in (diagonal for H, column for E/E~, row for F/F~), every lane
-// evaluates the state machine for "its" cell assuming the run continues, and one
-// ballot finds where the run really ends: a run of n equal steps costs one memory
-// round trip.  off[r] / off_end[r] of the reference are recomputed from r
+// 32 lanes speculatively fetch the next 32 x BT_DEPTH cells along the direction the
+// current state moves in (diagonal for H, column for E/E~, row for F/F~), every lane
+// evaluates the state machine for "its" cells assuming the run continues, and the
+// ballots find where the run really ends: a run of n equal steps costs
+// n / (32 x BT_DEPTH) memory round trips.  off[r] / off_end[r] of the reference are recomputed from r
 // (band_limits), so no per-row arrays are stored.  Two passes: count, then write into
 // an exactly-sized slice of the compact CIGAR arena (one atomicAdd per task).
 #pragma once
@@ -32,6 +32,8 @@ __device__ __forceinline__ int bt_next_state(int s, int cell, int force)
 
 // All 32 lanes of one warp call this.  Returns the number of CIGAR words; with WRITE it also stores
 // them (BAM encoding, len << 4 | op) at out[0 .. total).
+constexpr int BT_DEPTH = 4;      // cells each lane fetches per round of the speculative walk
+
 template <bool WRITE>
 __device__ int bt_walk(const TbPool& pool, const int32_t* table, const DevTask& T, int i0, int j0, uint32_t* out, int total)
 {
@@ -55,34 +57,50 @@ __device__ int bt_walk(const TbPool& pool, const int32_t* table, const DevTask& 
     auto op_of = [](int s) { return s == 0 ? 0 : ((s == 1 || s == 3) ? 2 : 1); };
 
     while (i >= 0 && j >= 0) {
-        // lane l looks at the cell l steps further along the direction of `state`
+        // lane l looks at the cells l, l + 32, ... (BT_DEPTH of them) steps further along the direction of `state`: the loads of
+        // one round are independent, so a run of n equal steps costs n / (32 * BT_DEPTH) memory round trips
         const int di = (state == 0 || state == 1 || state == 3) ? 1 : 0;
         const int dj = (state == 0 || state == 2 || state == 4) ? 1 : 0;
-        const int li = i - di * lane, lj = j - dj * lane;
-        const bool valid = li >= 0 && lj >= 0;
-        int ns = -1;
-        if (valid) {
-            int r = li + lj, st0, en0;
-            band_limits(r, T.qlen, T.tlen, T.w, st0, en0);
-            const int st = round_st(st0), en = round_en(en0);
-            int force = -1;
-            if (li < st) force = 2;
-            if (li > en) force = 1;
-            int cell = 0;
-            if (force < 0) {
-                cell = tb_row(pool, table, T.rows_per_page, T.pitch, r)[li - st];
-                // the DPX kernel stores the winner's priority code (tb_mode - d) in bits 0-2
-                if (T.tb_mode) cell = (cell & ~7) | (T.tb_mode - (cell & 7));
+        int ns[BT_DEPTH]; bool valid[BT_DEPTH];
+#pragma unroll
+        for (int k = 0; k < BT_DEPTH; ++k) {
+            const int step = lane + 32 * k;
+            const int li = i - di * step, lj = j - dj * step;
+            valid[k] = li >= 0 && lj >= 0;
+            ns[k] = -1;
+            if (valid[k]) {
+                int r = li + lj, st0, en0;
+                band_limits(r, T.qlen, T.tlen, T.w, st0, en0);
+                const int st = round_st(st0), en = round_en(en0);
+                int force = -1;
+                if (li < st) force = 2;
+                if (li > en) force = 1;
+                int cell = 0;
+                if (force < 0) {
+                    // (.cg: the rows of a segmented task were written on other SMs, into pages this SM may have read for an earlier task)
+                    cell = __ldcg(tb_row(pool, table, T.rows_per_page, T.pitch, r) + (li - st));
+                    // the DPX kernel stores the winner's priority code (tb_mode - d) in bits 0-2
+                    if (T.tb_mode) cell = (cell & ~7) | (T.tb_mode - (cell & 7));
+                }
+                ns[k] = bt_next_state(state, cell, force);
             }
-            ns = bt_next_state(state, cell, force);
         }
-        const unsigned cont = __ballot_sync(0xffffffffu, valid && ns == state);
-        int n = __ffs(~cont) - 1;            // leading lanes that stay in `state`
-        if (n < 0) n = 32;
+        int n = 0, ns_n = -1; bool valid_n = false, ended = false;
+#pragma unroll
+        for (int k = 0; k < BT_DEPTH; ++k) {
+            const unsigned cont = __ballot_sync(0xffffffffu, valid[k] && ns[k] == state);
+            int nk = __ffs(~cont) - 1;        // leading lanes of this group that stay in `state`
+            if (nk < 0) nk = 32;
+            const int src = nk < 32 ? nk : 0;
+            const int ns_k = __shfl_sync(0xffffffffu, ns[k], src);
+            const bool valid_k = __shfl_sync(0xffffffffu, (int)valid[k], src) != 0;
+            if (!ended) {
+                n += nk;
+                if (nk < 32) { ended = true; ns_n = ns_k; valid_n = valid_k; }
+            }
+        }
         if (n > 0) { emit(op_of(state), n); i -= di * n; j -= dj * n; }
-        if (n < 32) {
-            const int ns_n = __shfl_sync(0xffffffffu, ns, n);
-            const bool valid_n = __shfl_sync(0xffffffffu, (int)valid, n) != 0;
+        if (ended) {
             if (!valid_n) break;             // walked off the matrix
             state = ns_n;
             emit(op_of(state), 1);

@@ -57,11 +57,9 @@ struct fsv_ctx {
     int64_t segment_min_diags = -1;  // tasks with at least this many antidiagonals are cut into segments (0 = off, -1 = auto:
                                      // those whose chain of antidiagonals would outlast 60 % of the batch's throughput time)
     int segment_warm_pct = 400;      // cold-start lead of a segment, in percent of the band width (+1024 antidiagonals)
-    int segment_slots = 1;           // 1 = long tasks beyond the pool share re-use the static pages of earlier ones (in turn), 0 = they stay whole
-    int segment_align_pages = 1;     // 1 = segments are whole traceback pages, 0 = any multiple of 1024 antidiagonals
+    int segment_align_pages = 0;     // 0 = segments are multiples of 1024 antidiagonals (default), 1 = whole traceback pages
+    int segment_auto_pct = 35;       // auto mode: tasks whose chain of antidiagonals outlasts this share of the batch's throughput time are segmented
     int segment_extz = 1;            // auto mode: 1 = extension (EXTZ_ONLY) tasks are segmented too, 0 = global tasks only
-    int segment_pool_pct_bound = 25; // the same share when the batch's traceback does not fit the pool
-    int segment_pool_pct = 45;       // share of the traceback pool the segmented tasks' static pages may take
     int64_t segment_rows = 0;        // target antidiagonals per segment, rounded up to 1024 (0 = auto: 4 x or 2 x the warm-up)
     int lazy_min_pages = 16;    // DPX tasks with at least this many traceback pages take them as they advance (0 = all up front)
     int pool_stall_ms = 60000;  // lazy-pool watchdog
@@ -153,8 +151,8 @@ struct fsv_batch {
     // segmented tasks
     std::vector<DevSeg> segs;
     std::vector<SegTask> seg_tasks;
-    std::vector<int32_t> seg_pages;       // page-table entries (static pages from the top of the pool), per segmented task
-    int64_t seg_static_pages = 0, seg_rec_total = 0, seg_snap_words = 0;
+    int64_t seg_table_words = 0;          // page-table entries of the segmented tasks (filled on the device when a task is admitted)
+    int64_t seg_rec_total = 0, seg_snap_words = 0;
     struct SegLaunch { int nw, begin, count; };
     std::vector<SegLaunch> seg_launches;  // slices of seg_work
     std::vector<int32_t> seg_work;        // segment indices per launch
@@ -258,11 +256,10 @@ extern "C" int fsv_set_option(fsv_ctx* c, const char* key, int64_t value)
     }
     if (!strcmp(key, "segment_min_diags")) { if (value < -1) return FSV_ERR_INVALID; c->segment_min_diags = value; return FSV_OK; }
     if (!strcmp(key, "segment_warm_pct")) { if (value < 50 || value > 2000) return FSV_ERR_INVALID; c->segment_warm_pct = (int)value; return FSV_OK; }
-    if (!strcmp(key, "segment_slots")) { c->segment_slots = value != 0; return FSV_OK; }
+    if (!strcmp(key, "segment_slots") || !strcmp(key, "segment_pool_pct") || !strcmp(key, "segment_pool_pct_bound")) return FSV_OK;   // ABI 3 tunables of the static page slots: accepted, no effect
+    if (!strcmp(key, "segment_auto_pct")) { if (value < 1 || value > 1000) return FSV_ERR_INVALID; c->segment_auto_pct = (int)value; return FSV_OK; }
     if (!strcmp(key, "segment_align_pages")) { c->segment_align_pages = value != 0; return FSV_OK; }
     if (!strcmp(key, "segment_extz")) { c->segment_extz = value != 0; return FSV_OK; }
-    if (!strcmp(key, "segment_pool_pct_bound")) { if (value < 1 || value > 90) return FSV_ERR_INVALID; c->segment_pool_pct_bound = (int)value; return FSV_OK; }
-    if (!strcmp(key, "segment_pool_pct")) { if (value < 1 || value > 90) return FSV_ERR_INVALID; c->segment_pool_pct = (int)value; return FSV_OK; }
     if (!strcmp(key, "segment_rows")) { if (value != 0 && value < 1024) return FSV_ERR_INVALID; c->segment_rows = value; return FSV_OK; }
     if (!strcmp(key, "pool_stall_ms")) { if (value < 100) return FSV_ERR_INVALID; c->pool_stall_ms = (int)value; return FSV_OK; }
     if (!strcmp(key, "lazy_fill_pct")) {
@@ -514,12 +511,14 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
     std::vector<int32_t> ord(n);
     for (size_t i = 0; i < n; ++i) ord[i] = (int32_t)i;
     std::stable_sort(ord.begin(), ord.end(), [&](int32_t a, int32_t x) { return b->tasks[a].cells_est > b->tasks[x].cells_est; });
-    // ---- segmented tasks (fsv_common.cuh, DevSeg): the longest left-aligned CIGAR tasks are cut into segments of whole
-    // traceback pages; their pages are static (taken from the top of the pool), at most 45 % of it
+    // ---- segmented tasks (fsv_common.cuh, DevSeg): left-aligned CIGAR tasks whose chain of antidiagonals is long against the
+    // batch are cut into segments that run on separate CTAs.  Their traceback comes from the dynamic pool like everybody
+    // else's (all pages of a task at once, when its first segment starts), so how many are segmented is a question of work only:
+    // a segment costs warm / seg_rows extra cells, a whole task that starts late keeps one CTA busy after the batch has ended.
     std::vector<uint8_t> is_seg(n, 0);
     if (c->segment_min_diags != 0) {
-        // auto: the batch's throughput time if every SM were full (SM-seconds model of the exclusive planning below);
-        // a task whose own chain would outlast 60 % of it (or of 20 ms) is worth cutting up
+        // auto: the batch's throughput time if every SM were full (SM-seconds model of the exclusive planning below); a task whose
+        // own chain would outlast `segment_auto_pct` % of it (or of 20 ms) is cut up
         int64_t min_diags = c->segment_min_diags;
         double W = 0;
         for (size_t i = 0; i < n; ++i) if (b->is_dpx[i]) {
@@ -527,110 +526,64 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
             W += (double)(b->tasks[i].qlen + b->tasks[i].tlen) * (nw <= 2 ? 2.0e-6 : nw == 4 ? 1.8e-6 : 1.55e-6) / (nw == 1 ? 12.0 : nw == 2 ? 6.0 : nw == 4 ? 3.0 : 2.0);
         }
         const double t_thr = std::max(W / c->sm_count, 0.020);
-        if (min_diags < 0) min_diags = (int64_t)(0.6 * t_thr / 1.55e-6);
+        if (min_diags < 0) min_diags = (int64_t)(c->segment_auto_pct * 0.01 * t_thr / 1.55e-6);
         std::vector<int32_t> by_len;
         for (size_t i = 0; i < n; ++i) {
             const DevTask& d = b->tasks[i];
             if (b->is_dpx[i] && d.tb_pages > 0 && !(d.flag & (FSV_EZ_RIGHT | FSV_EZ_SCORE_ONLY | FSV_EZ_APPROX_MAX)) && d.w >= 64 &&
-                (int64_t)d.qlen + d.tlen - 1 >= min_diags &&
-                !(c->segment_min_diags < 0 && !c->segment_extz && (d.flag & FSV_EZ_EXTZ_ONLY)))      // an extension may end early by z-drop and its later segments are then wasted work: only tasks that decide the batch time anyway get here
+                (int64_t)d.qlen + d.tlen - 1 >= min_diags && d.tb_pages <= b->pool_pages &&
+                !(c->segment_min_diags < 0 && !c->segment_extz && (d.flag & FSV_EZ_EXTZ_ONLY)))
                 by_len.push_back((int32_t)i);
         }
         std::stable_sort(by_len.begin(), by_len.end(), [&](int32_t a, int32_t x) { return b->tasks[a].qlen + b->tasks[a].tlen > b->tasks[x].qlen + b->tasks[x].tlen; });
         std::vector<std::vector<int32_t>> per_nw(9);
-        struct SegPlan { int32_t ti; int64_t seg_rows, warm; int n_segs; int slot; };
-        // The static region is a few SLOTS: the longest tasks get one each while the pool share lasts, the next ones re-use the slot
-        // of an earlier task of the same warp class (same work queue, so that task's segments were all taken before theirs) and
-        // wait on the device for its stitch to end.  A batch with many long tasks then works through them a few at a time, every
-        // SM on their segments, instead of leaving all but the first few whole.
-        struct SegSlot { int64_t base, size; int nw, users, last_user, first_table_off; };
-        std::vector<SegSlot> slots;
+        struct SegPlan { int32_t ti; int64_t seg_rows, warm; int n_segs; };
         std::vector<SegPlan> plan;
-        {
-            // static pages: a share of the pool; smaller when the batch's traceback does not fit the pool anyway (then the
-            // pool, not the longest chain, is what the batch waits for: measured on cfg2, 25 % is neutral, 45 % costs 14 %)
-            // ... unless the longest chain alone is more than twice the batch's throughput time: then the chain is what the
-            // batch waits for whatever the pool does (cfg4 at 1/4 scale: 3.5 s whole, 1.29 s with 25 %, 0.87 s with 45 %)
-            const bool chain_bound = !by_len.empty() && (double)(b->tasks[(size_t)by_len[0]].qlen + b->tasks[(size_t)by_len[0]].tlen) * 1.3e-6 > 2.0 * t_thr;
-            const int pct = b->pages_total > b->cap_pages && !chain_bound ? std::min(c->segment_pool_pct, c->segment_pool_pct_bound) : c->segment_pool_pct;
-            int64_t pages = 0, longest_in = 0, longest_out = 0;
-            // segments of 4 x warm rows cost 25 % more cells; if that leaves most SMs without a segment (a handful of long
-            // tasks: cfg1's two contigs make 16), halve them: 2 x warm rows, 50 % more cells on SMs that would idle anyway
-            int total_segs = 0;
-            for (int mult = 4; mult >= 2; mult -= 2) {
-                plan.clear(); slots.clear(); pages = longest_in = longest_out = 0; total_segs = 0;
-                for (int32_t ti : by_len) {
-                    const DevTask& d = b->tasks[(size_t)ti];
-                    const int64_t n_diag = (int64_t)d.qlen + d.tlen - 1;
-                    const int64_t warm = (int64_t)c->segment_warm_pct * d.w / 100 + 1024;                    // generous: a flat cold start is bit-identical well within it (fallback if not)
-                    const int64_t want = c->segment_rows > 0 ? c->segment_rows : std::max<int64_t>(mult * warm, 16384);
-                    // whole pages by default.  (The pages are static, so segments could share them: `segment_align_pages` 0 cuts narrow-band
-                    // tasks four times finer - cfg3's reads 146 -> 74 ms, cfg1's 50 -> 32 ms - but with that many more boundaries some
-                    // fail their check and the whole-task fallback costs more than was won: off until a failed boundary is cheap.)
-                    const int64_t rpp = d.rows_per_page;
-                    const int64_t seg_rows = c->segment_align_pages ? std::max<int64_t>(1, (want + rpp - 1) / rpp) * rpp : (want + 1023) / 1024 * 1024;
-                    const int n_segs = (int)((n_diag + seg_rows - 1) / seg_rows);
-                    if (n_segs < 2 || seg_rows < 2 * warm) continue;
-                    int slot = -1;
-                    if ((pages + d.tb_pages) * 100 <= b->cap_pages * pct) {
-                        slot = (int)slots.size();
-                        slots.push_back({pages, d.tb_pages, d.nw, 0, -1, -1});
-                        pages += d.tb_pages;
-                    } else if (c->segment_slots && (double)n_diag * 1.3e-6 > 2.0 * t_thr) {
-                        // (only chains the batch cannot hide anyway: re-using slots for every eligible task makes the medium ones queue
-                        // behind each other's stitch while they could have run whole side by side - cfg4 at 1/4 scale 840 -> 1 515 ms)
-                        for (size_t k = 0; k < slots.size(); ++k)
-                            if (slots[k].nw == d.nw && slots[k].size >= d.tb_pages && (slot < 0 || slots[k].users < slots[(size_t)slot].users)) slot = (int)k;
-                    }
-                    if (slot < 0) { longest_out = std::max(longest_out, n_diag); continue; }
-                    ++slots[(size_t)slot].users;
-                    longest_in = std::max(longest_in, n_diag);
-                    plan.push_back({ti, seg_rows, warm, n_segs, slot});
-                    total_segs += n_segs;
-                }
-                if (c->segment_rows > 0 || total_segs >= c->sm_count) break;
+        int total_segs = 0;
+        // segments of 4 x warm rows cost 25 % more cells; if that leaves most SMs without a segment (a handful of long
+        // tasks: cfg1's two contigs make 16), halve them: 2 x warm rows, 50 % more cells on SMs that would idle anyway
+        for (int mult = 4; mult >= 2; mult -= 2) {
+            plan.clear(); total_segs = 0;
+            for (int32_t ti : by_len) {
+                const DevTask& d = b->tasks[(size_t)ti];
+                const int64_t n_diag = (int64_t)d.qlen + d.tlen - 1;
+                const int64_t warm = (int64_t)c->segment_warm_pct * d.w / 100 + 1024;      // a flat cold start is bit-identical well within it; a boundary that is not is repaired
+                const int64_t want = c->segment_rows > 0 ? c->segment_rows : std::max<int64_t>(mult * warm, 16384);
+                const int64_t rpp = d.rows_per_page;
+                const int64_t seg_rows = c->segment_align_pages ? std::max<int64_t>(1, (want + rpp - 1) / rpp) * rpp : (want + 1023) / 1024 * 1024;
+                const int n_segs = (int)((n_diag + seg_rows - 1) / seg_rows);
+                if (n_segs < 2 || seg_rows < 2 * warm) continue;
+                plan.push_back({ti, seg_rows, warm, n_segs});
+                total_segs += n_segs;
             }
-            const size_t planned = plan.size();
-            // a chain-bound batch still waits for the longest task that stays WHOLE: if the pool share ran out before the chains got
-            // markedly shorter, the segments only take pages away from it (full-size cfg4, 9.4 M-antidiagonal tasks of 29 GB each:
-            // 18.1 s whole, 22.3 s with three tasks segmented, 38 s with four) - leave every task whole
-            if (c->segment_min_diags < 0 && chain_bound && longest_out * 10 > longest_in * 7) { plan.clear(); slots.clear(); total_segs = 0; }
-            if (getenv("FSV_TRACE"))
-                fprintf(stderr, "[fsv] segment plan: min_diags %lld, eligible %zu, within the pool share (%d %%) %zu (%lld pages of %lld), longest in %lld / left whole %lld -> %zu tasks in %d segments\n",
-                        (long long)min_diags, by_len.size(), pct, planned, (long long)pages, (long long)b->cap_pages, (long long)longest_in, (long long)longest_out, plan.size(), total_segs);
+            if (c->segment_rows > 0 || total_segs >= c->sm_count) break;
         }
+        if (getenv("FSV_TRACE"))
+            fprintf(stderr, "[fsv] segment plan: throughput time %.3f s, min_diags %lld, eligible %zu -> %zu tasks in %d segments\n",
+                    t_thr, (long long)min_diags, by_len.size(), plan.size(), total_segs);
+        std::vector<int> n_in_class(9, 0);
         for (const SegPlan& sp : plan) {
             const int32_t ti = sp.ti;
             DevTask& d = b->tasks[(size_t)ti];
             const int64_t n_diag = (int64_t)d.qlen + d.tlen - 1;
-            const int64_t warm = sp.warm, seg_rows = sp.seg_rows;
-            const int n_segs = sp.n_segs;
             SegTask st{};
-            st.rec_off = b->seg_rec_total; st.snap_off = b->seg_snap_words; st.table_off = (int32_t)b->seg_pages.size();
-            st.n_segs = n_segs; st.first_seg = (int32_t)b->segs.size();
+            st.rec_off = b->seg_rec_total; st.snap_off = b->seg_snap_words; st.table_off = (int32_t)b->seg_table_words;
+            st.n_segs = sp.n_segs; st.first_seg = (int32_t)b->segs.size();
+            st.ticket = n_in_class[(size_t)d.nw]++;                 // admission order inside its launch = queue order
             b->seg_rec_total += n_diag;
-            b->seg_snap_words += (int64_t)2 * (n_segs - 1) * SEG_SNAP_WORDS;
-            SegSlot& sl = slots[(size_t)sp.slot];
-            for (int pg = 0; pg < d.tb_pages; ++pg) b->seg_pages.push_back((int32_t)(b->pool_pages - 1 - (sl.base + pg)));
-            if (sl.first_table_off < 0) sl.first_table_off = st.table_off;      // the first user's table lists the whole slot
-            st.wait_for = sl.last_user; st.free_table_off = 0; st.free_pages = 0;
-            sl.last_user = (int)b->seg_tasks.size();
+            b->seg_snap_words += (int64_t)2 * (sp.n_segs - 1) * SEG_SNAP_WORDS;
+            b->seg_table_words += d.tb_pages;
             d.seg_id = (int32_t)b->seg_tasks.size();
-            for (int k = 0; k < n_segs; ++k) {
+            for (int k = 0; k < sp.n_segs; ++k) {
                 DevSeg g{};
-                g.task = ti; g.index = k; g.count = n_segs;
-                g.r_begin = (int32_t)(k * seg_rows); g.r_end = (int32_t)std::min<int64_t>((k + 1) * seg_rows, n_diag);
-                g.r0 = (int32_t)std::max<int64_t>(0, g.r_begin - warm);
+                g.task = ti; g.index = k; g.count = sp.n_segs;
+                g.r_begin = (int32_t)(k * sp.seg_rows); g.r_end = (int32_t)std::min<int64_t>((k + 1) * sp.seg_rows, n_diag);
+                g.r0 = (int32_t)std::max<int64_t>(0, g.r_begin - sp.warm);
                 per_nw[(size_t)d.nw].push_back((int32_t)b->segs.size());
                 b->segs.push_back(g);
             }
             b->seg_tasks.push_back(st);
             is_seg[(size_t)ti] = 1;
-        }
-        for (const SegSlot& sl : slots) if (sl.last_user >= 0) {
-            b->seg_tasks[(size_t)sl.last_user].free_table_off = sl.first_table_off;
-            b->seg_tasks[(size_t)sl.last_user].free_pages = (int32_t)sl.size;
-            b->seg_static_pages += sl.size;
         }
         for (int nw = 8; nw >= 1; --nw) if (!per_nw[(size_t)nw].empty()) {
             b->seg_launches.push_back({nw, (int)b->seg_work.size(), (int)per_nw[(size_t)nw].size()});
@@ -727,9 +680,9 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
     if (!b->segs.empty()) {
         DEV(d_segs, sz_seg[0], b->segs.size() * sizeof(DevSeg));
         DEV(d_seg_tasks, sz_seg[1], b->seg_tasks.size() * sizeof(SegTask));
-        DEV(d_seg_tables, sz_seg[2], b->seg_pages.size() * 4 + 16);
+        DEV(d_seg_tables, sz_seg[2], (size_t)b->seg_table_words * 4 + 16);
         DEV(d_seg_work, sz_seg[3], b->seg_work.size() * 4 + 16);
-        DEV(d_seg_done, sz_seg[4], b->seg_tasks.size() * 12 + 16);      // done counters, cancel flags, released flags
+        DEV(d_seg_done, sz_seg[4], b->seg_tasks.size() * 12 + 64);      // done counters, cancel flags, admitted flags, ticket counters (one per launch)
         DEV(d_seg_foot, sz_seg[5], b->segs.size() * 4 + 16);
         DEV(d_seg_rec, sz_seg[6], (size_t)b->seg_rec_total * sizeof(int4) + 16);
         DEV(d_seg_snap, sz_seg[7], (size_t)b->seg_snap_words * 4 + 16);
@@ -745,7 +698,6 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
         if (!b->segs.empty()) {
             CKB(cudaMemcpyAsync(b->d_segs, b->segs.data(), b->segs.size() * sizeof(DevSeg), cudaMemcpyHostToDevice, c->stream));
             CKB(cudaMemcpyAsync(b->d_seg_tasks, b->seg_tasks.data(), b->seg_tasks.size() * sizeof(SegTask), cudaMemcpyHostToDevice, c->stream));
-            CKB(cudaMemcpyAsync(b->d_seg_tables, b->seg_pages.data(), b->seg_pages.size() * 4, cudaMemcpyHostToDevice, c->stream));
             CKB(cudaMemcpyAsync(b->d_seg_work, b->seg_work.data(), b->seg_work.size() * 4, cudaMemcpyHostToDevice, c->stream));
         }
     }
@@ -793,7 +745,7 @@ extern "C" int fsv_batch_run(fsv_batch* b)
     CK(c, cudaMemsetAsync(c->d_lazy, 0, sizeof(LazyState), c->stream));
     CK(c, cudaMemsetAsync(reinterpret_cast<uint8_t*>(c->d_lazy) + sizeof(LazyState), 0xff, (size_t)(n_slots + 1) * 4, c->stream));
     {   // control block: overflow flag, pool lock, free count, queue states; free stack = every page
-        const int64_t dyn_pages = b->pool_pages - b->seg_static_pages;      // segmented tasks own the top of the pool
+        const int64_t dyn_pages = b->pool_pages;
         std::vector<int32_t> stack((size_t)b->pool_pages + 1);
         for (int64_t i = 0; i < dyn_pages; ++i) stack[(size_t)i] = (int32_t)i;
         CK(c, cudaMemcpyAsync(c->d_free_stack, stack.data(), (size_t)(b->pool_pages + 1) * 4, cudaMemcpyHostToDevice, c->stream));
@@ -808,7 +760,8 @@ extern "C" int fsv_batch_run(fsv_batch* b)
             memcpy(&ctrl[8 + 2 * (b->launches.size() + i)], &st, 8);
         }
         if (!b->segs.empty()) {
-            CK(c, cudaMemsetAsync(b->d_seg_done, 0, b->seg_tasks.size() * 12, c->stream));
+            CK(c, cudaMemsetAsync(b->d_seg_done, 0, b->seg_tasks.size() * 12 + 64, c->stream));
+            CK(c, cudaMemsetAsync(b->d_seg_tables, 0xff, (size_t)b->seg_table_words * 4, c->stream));
             CK(c, cudaMemsetAsync(b->d_seg_foot, 0xff, b->segs.size() * 4, c->stream));
             CK(c, cudaMemsetAsync(b->d_seg_snap, 0, (size_t)b->seg_snap_words * 4, c->stream));
         }
@@ -819,8 +772,8 @@ extern "C" int fsv_batch_run(fsv_batch* b)
     tr.lap("run: scratch + control block");
     RunCtx R{};
     R.qarena = b->d_q; R.tarena = b->d_t; R.tasks = b->d_tasks; R.results = b->d_results;
-    R.pool.base = c->d_pool; R.pool.page_bytes = c->page_bytes; R.pool.n_pages = (int32_t)(b->pool_pages - b->seg_static_pages);
-    R.pool.free_stack = c->d_free_stack; R.pool.n_free = b->d_ctrl + 2; R.pool.lock = b->d_ctrl + 1; R.pool.progress = b->d_ctrl + 3; R.pool.gate = b->d_ctrl + 4;
+    R.pool.base = c->d_pool; R.pool.page_bytes = c->page_bytes; R.pool.n_pages = (int32_t)b->pool_pages;
+    R.pool.free_stack = c->d_free_stack; R.pool.n_free = b->d_ctrl + 2; R.pool.lock = b->d_ctrl + 1; R.pool.progress = b->d_ctrl + 3; R.pool.gate = b->d_ctrl + 4; R.pool.reserve = b->d_ctrl + 5;
     // lazy growth only pays (and only costs) when the batch's traceback does not fit the pool at once
     const bool lazy_on = c->lazy_min_pages > 0 && b->pool_pages < b->pages_total;      // (static pages of segmented tasks count on both sides)
     R.pool.lazy = lazy_on ? reinterpret_cast<LazyState*>(c->d_lazy) : nullptr;
@@ -834,7 +787,7 @@ extern "C" int fsv_batch_run(fsv_batch* b)
     R.timeline = b->d_timeline;
     R.sc = b->sc;
     R.segs = b->d_segs; R.seg_tasks = b->d_seg_tasks; R.seg_rec = b->d_seg_rec; R.seg_snap = b->d_seg_snap;
-    R.seg_tables = b->d_seg_tables; R.seg_done = b->d_seg_done; R.seg_cancel = b->d_seg_done + b->seg_tasks.size(); R.seg_released = b->d_seg_done + 2 * b->seg_tasks.size(); R.seg_foot = b->d_seg_foot;
+    R.seg_tables = b->d_seg_tables; R.seg_done = b->d_seg_done; R.seg_cancel = b->d_seg_done + b->seg_tasks.size(); R.seg_admitted = b->d_seg_done + 2 * b->seg_tasks.size(); R.seg_ticket = b->d_seg_done + 3 * b->seg_tasks.size(); R.seg_foot = b->d_seg_foot;
 
     // events of this run, destroyed on every way out
     struct Events {
@@ -858,7 +811,7 @@ extern "C" int fsv_batch_run(fsv_batch* b)
         CK(c, cudaStreamWaitEvent(ks, e0, 0));
         TaskQueue Q{reinterpret_cast<unsigned long long*>(b->d_ctrl + 8 + 2 * qi), b->d_seg_work + L.begin};
         R.page_tables = c->d_tables; R.slot_base = 0;
-        DpxParams D{R, Q, DpxK{}};
+        DpxParams D{R, Q, DpxK{}, (int32_t)i};
         rc = b->dual ? dpx_launch_seg_1(ks, c->sm_count, L.nw, L.count, D, &c->last_error) : dpx_launch_seg_0(ks, c->sm_count, L.nw, L.count, D, &c->last_error);
         if (rc != FSV_OK) return rc;
         c->stats.fill_launches++;
@@ -876,7 +829,7 @@ extern "C" int fsv_batch_run(fsv_batch* b)
         R.page_tables = c->d_tables + L.table_off;
         R.slot_base = slot_base; slot_base += L.grid;
         if (L.kind == 1) {
-            DpxParams D{R, Q, DpxK{}};
+            DpxParams D{R, Q, DpxK{}, 0};
             rc = dpx_launch(ks, b->dual, L.with_tb, L.nw, L.grid, L.excl != 0, D, &c->last_error);
             if (rc != FSV_OK) return rc;
         } else {
@@ -909,7 +862,7 @@ extern "C" int fsv_batch_run(fsv_batch* b)
     if (!b->seg_tasks.empty()) {
         std::vector<int32_t> sd(b->seg_tasks.size());
         CK(c, cudaMemcpy(sd.data(), b->d_seg_done, sd.size() * 4, cudaMemcpyDeviceToHost));
-        for (int32_t v : sd) c->stats.segment_fallbacks += v >= (1 << 20);
+        for (int32_t v : sd) c->stats.segment_fallbacks += v >> 20;      // repaired segments
     }
     c->stats.tasks += (int64_t)b->n;
     int64_t ne = 0;

@@ -125,6 +125,8 @@ struct TbPool {
     int32_t* lock;          // 0 = free
     int32_t* progress;      // bumped (under the lock) by every grant and every release: the stall watchdog's heartbeat
     int32_t* gate;          // waiters for memory poll ONE at a time (the checks run under the pool lock)
+    int32_t* reserve;       // pages a segmented task is waiting for (its whole traceback, taken at once): no NEW ordinary task starts
+                            // unless that many stay free (running tasks still grow, so nothing can deadlock on it)
     LazyState* lazy;        // null = every task takes its pages up front
     int32_t* slot_idx;      // per CTA slot: index into lazy->* of the task it runs, or -1
     int32_t lazy_min_pages; // tasks with at least this many pages grow lazily (<= 0: none)
@@ -187,13 +189,15 @@ __device__ inline float lazy_projected_peak(const TbPool& P, int new_total, int 
 
 // All of these are called by ONE thread of a CTA.
 // Up-front allocation of n pages; false when they are not free or would endanger the lazy tasks.
-__device__ inline bool pool_try_alloc(const TbPool& P, int n, int32_t* table)
+// `for_seg`: the caller is the one segmented task whose turn it is (it owns the reserve and ignores it).
+__device__ inline bool pool_try_alloc(const TbPool& P, int n, int32_t* table, bool for_seg = false)
 {
     if (n <= 0) return true;
     bool ok = false;
     pool_lock(P.lock);
     int nf = *(volatile int32_t*)P.n_free;
-    if (nf >= n && (!P.lazy || ((volatile LazyState*)P.lazy)->n == 0 || lazy_safe(P, nf - n, -1, 0))) {
+    const int keep = for_seg ? 0 : *(volatile int32_t*)P.reserve;
+    if (nf - n >= keep && (!P.lazy || ((volatile LazyState*)P.lazy)->n == 0 || lazy_safe(P, nf - n, -1, 0))) {
         for (int i = 0; i < n; ++i) table[i] = ((volatile int32_t*)P.free_stack)[nf - 1 - i];
         *(volatile int32_t*)P.n_free = nf - n;
         ++*(volatile int32_t*)P.progress;
@@ -210,7 +214,7 @@ __device__ inline bool pool_lazy_admit(const TbPool& P, int slot, int total, int
     pool_lock(P.lock);
     volatile LazyState* L = P.lazy;
     const int nf = *(volatile int32_t*)P.n_free, n = L->n;
-    if (nf >= first && n < LAZY_MAX) {
+    if (nf - first >= *(volatile int32_t*)P.reserve && n < LAZY_MAX) {
         bool fits = n == 0 || lazy_projected_peak(P, total, rpp) <= P.lazy_fill * (float)P.n_pages;
         if (fits) {
             L->held[n] = first; L->total[n] = total; L->rpp[n] = rpp; L->slot[n] = slot; L->n = n + 1;
@@ -288,13 +292,16 @@ __device__ inline int queue_take(const TaskQueue& Q, int end)
 }
 
 // ---------------------------------------------------------------------------
-// Segmented tasks.  The difference recurrence forgets its start after about 2w antidiagonals (DESIGN.md section 6,
-// scripts/convergence_probe.py), so a long task is cut into segments (rows of a static page table, so they may share pages) that run on
-// different CTAs at the same time: segment s > 0 starts COLD `warm` antidiagonals before its first own row, writes
-// traceback rows and one record per antidiagonal from its first own row on, and dumps its state at its first and
-// last own rows.  The CTA that finishes the task's last segment checks every boundary bit for bit (the state a
-// segment reached cold == the state its predecessor reached from the truth), chains the score offsets, replays the
-// ksw_extz_t bookkeeping over the records and walks the CIGAR; any mismatch re-runs the task unsegmented.
+// Segmented tasks.  The difference recurrence forgets its start after about 2w antidiagonals (DESIGN.md section 3.7,
+// scripts/convergence_probe.py), so a long task is cut into segments that run on different CTAs at the same time:
+// segment s > 0 starts COLD `warm` antidiagonals before its first own row, writes traceback rows and one record per
+// antidiagonal from its first own row on, and dumps its state at its first and last own rows.  The task's traceback
+// pages come from the dynamic pool, all at once, when its first segment starts (tasks take their turn in queue order
+// and the one waiting holds a reserve against new ordinary tasks), and go back when its CIGAR is written.  The CTA that
+// finishes the task's last segment replays the ksw_extz_t bookkeeping over the records, checks the boundaries below the
+// segment the alignment ends in bit for bit (the state a segment reached cold == the state its predecessor reached from
+// the truth), and walks the CIGAR.  A boundary that does not hold is REPAIRED: the same CTA runs the upper segment again,
+// this time from its predecessor's end state (exact by construction), and checks on from there.
 struct DevSeg {
     int32_t task;               // index into tasks[]
     int32_t index, count;       // this segment, segments of the task
@@ -304,13 +311,12 @@ struct DevSeg {
 struct SegTask {
     int64_t rec_off;            // into seg_rec: one int4 per antidiagonal {max H, argmax column, H[en0] | NEG_INF, H[st0] | NEG_INF}
     int64_t snap_off;           // into seg_snap (words): boundary b = slots 2b (last row of segment b) and 2b+1 (warm end of b+1)
-    int32_t table_off;          // into seg_tables: the task's page table (static pages, all rows)
+    int32_t table_off;          // into seg_tables: the task's page table (all rows; filled when the task is admitted)
     int32_t n_segs, first_seg;
-    int32_t wait_for;           // the segmented task that used this task's static pages before it (its segments wait for that one's
-                                // stitch to end), or -1: the static region is a few SLOTS that the long tasks of a warp class take turns in
-    int32_t free_table_off, free_pages;   // last user of a slot: the slot's pages, returned to the dynamic pool after the stitch (else 0)
+    int32_t ticket;             // admission order of the segmented tasks (= their order in the segment queue)
 };
-constexpr int SEG_SNAP_HDR = 8;                 // words: anchor H (lane st0), valid flag
+constexpr int SEG_SNAP_HDR = 8;                 // words: anchor H (lane st0), valid flag, "repaired" flag (slot 2b+1: segment b+1 was run again
+                                                // from segment b's end state, so boundary b holds by construction and both share one score frame)
 constexpr int SEG_SNAP_PER_THREAD = 67;         // 64 state words, Vt, Hb, reserved
 constexpr int SEG_SNAP_WORDS = SEG_SNAP_HDR + 256 * SEG_SNAP_PER_THREAD;
 
@@ -336,9 +342,10 @@ struct RunCtx {
     int4* seg_rec;
     uint32_t* seg_snap;
     const int32_t* seg_tables;
-    int32_t* seg_done;           // per segmented task: segments finished
-    int32_t* seg_released;       // per segmented task: its stitch is over and its static pages may be written by the slot's next user
+    int32_t* seg_done;           // per segmented task: segments finished (+ 1 << 20 per repaired segment, counted by the host)
+    int32_t* seg_admitted;       // per segmented task: its traceback pages are in its table (set by the CTA that runs its segment 0)
     int32_t* seg_cancel;         // per segmented task: set by segment 0 when the alignment z-drops inside it; the other segments poll it and stop
+    int32_t* seg_ticket;         // ticket of the segmented task whose turn it is to take its pages
     int32_t* seg_foot;           // per segment: antidiagonal at which the band ran out inside it, or -1
 };
 
@@ -435,7 +442,8 @@ static __device__ __noinline__ int pool_lazy_grow(const TbPool& P, int slot, int
 __device__ __forceinline__ uint8_t* tb_row(const TbPool& P, const int32_t* table, int rows_per_page, int pitch, int r)
 {
     const int pg = r / rows_per_page;
-    return P.base + (int64_t)table[pg] * P.page_bytes + (int64_t)(r - pg * rows_per_page) * pitch;
+    // (__ldcg: a segmented task's table is written by the CTA that admitted it, possibly on another SM, and L1 lines are shared by tables)
+    return P.base + (int64_t)__ldcg(table + pg) * P.page_bytes + (int64_t)(r - pg * rows_per_page) * pitch;
 }
 
 }  // namespace fsv

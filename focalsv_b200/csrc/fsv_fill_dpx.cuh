@@ -43,6 +43,7 @@ struct DpxParams {
     RunCtx C;
     TaskQueue Q;
     DpxK K;
+    int32_t seg_launch;         // SEG launches: which ticket counter (one per launch: a launch's CTAs only ever wait for tasks of their own queue)
 };
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
@@ -230,13 +231,30 @@ __device__ __forceinline__ void dpx_cells(uint32_t (&U)[8], uint32_t (&V)[8], ui
 // shared memory reserved, so that a CTA working on one of the few very long tasks has its SM to itself.
 // TBM: 0 = score only, 1 = traceback, ties to the left (default), 2 = traceback, ties to the right (KSW_EZ_RIGHT),
 // 3 = score only with KSW_EZ_APPROX_MAX (:270-286): no H[] at all, one cell is followed greedily.
-// End of a segmented task (one thread): the slot's next user may start; the slot's LAST user returns its pages to the dynamic pool.
-__device__ __forceinline__ void seg_release(const RunCtx& C, int seg_id)
+// End of a segmented task (one thread): its traceback pages go back to the pool.
+__device__ __forceinline__ void seg_release(const RunCtx& C, const DevTask& T, const int32_t* table)
 {
-    const SegTask ST = C.seg_tasks[seg_id];
-    if (ST.free_pages > 0) pool_free(C.pool, ST.free_pages, const_cast<int32_t*>(C.seg_tables) + ST.free_table_off);
+    pool_free(C.pool, T.tb_pages, table);
+}
+
+// A segmented task takes ALL its traceback pages at once when its first segment starts (thread 0 of that CTA), in the order of
+// the segment queue (tickets): a task either holds everything it needs or nothing, so the segments of the tasks in flight can
+// always finish.  While it waits it holds a reserve that keeps NEW ordinary tasks from starting (running ones still grow).
+static __device__ __noinline__ void seg_admit(const RunCtx& C, const DevTask& T, const SegTask& ST, int32_t* table, int32_t* ticket)
+{
+    StallWatch watch;
+    unsigned ns = 128;
+    while (*(volatile int32_t*)ticket != ST.ticket) { __nanosleep(ns); if (ns < 4096) ns <<= 1; }
+    for (;;) {
+        atomicMax(C.pool.reserve, T.tb_pages);
+        if (pool_try_alloc(C.pool, T.tb_pages, table, true)) break;
+        __nanosleep(4000);
+        watch.poll(C.pool);
+    }
+    atomicExch(C.pool.reserve, 0);
     __threadfence();
-    atomicExch(C.seg_released + seg_id, 1);
+    atomicExch(C.seg_admitted + T.seg_id, 1);
+    atomicAdd(ticket, 1);
 }
 
 // SEG: the launch works on SEGMENTS of long tasks (fsv_common.cuh, DevSeg): P.Q holds segment indices.
@@ -269,7 +287,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
     const uint32_t extSel = DUAL ? 0xB391u : 0x4341u;                  // int8 (signed / unsigned) -> int16
     int32_t* table = C.page_tables + (int64_t)blockIdx.x * C.max_pages_per_task;
     int pending = -1;
-    int seg_redo = -1;          // SEG: segment index whose task failed the boundary check and is re-run whole by this CTA
+    int seg_redo = -1;          // SEG: a segment whose cold start did not reach its predecessor's state: this CTA runs it again FROM that state
 
     for (;;) {
         __syncthreads();
@@ -282,23 +300,26 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
         __syncthreads();
         const int wi = (int)lds32(sb + OFF_TASK);      // task index, or (SEG) segment index
         if (wi < 0) return;
-        // a segment of a long task, or (seg_redo) the whole task again on its static page table
+        // a segment of a long task: from its cold start, or (seg_redo) again from its predecessor's end state ("repair")
         DevSeg G{wi, 0, 1, 0, 0, 0};
         if (SEG) G = C.segs[wi];
         const int ti = G.task;
         const DevTask T = C.tasks[ti];
-        const bool segmode = SEG && seg_redo < 0;
-        if (SEG) { table = const_cast<int32_t*>(C.seg_tables) + C.seg_tasks[T.seg_id].table_off; seg_redo = -1; }
-        if (SEG && segmode) {
-            // the task's static pages are a slot an earlier task of this queue may still be reading (its CIGAR walk): wait for
-            // that task's stitch.  Its segments were all taken from this queue before this one, so they are running or done.
-            const int wf = C.seg_tasks[T.seg_id].wait_for;
-            if (wf >= 0) {
-                if (tid == 0) { unsigned ns = 256; while (__ldcg(C.seg_released + wf) == 0) { __nanosleep(ns); if (ns < 8192) ns <<= 1; } __threadfence(); }
+        const bool segmode = SEG;
+        const bool repair = SEG && seg_redo >= 0;
+        if (SEG) {
+            const SegTask& STa = C.seg_tasks[T.seg_id];
+            table = const_cast<int32_t*>(C.seg_tables) + STa.table_off;
+            seg_redo = -1;
+            if (!repair) {
+                if (tid == 0) {
+                    if (G.index == 0) seg_admit(C, T, STa, table, C.seg_ticket + P.seg_launch);
+                    else { unsigned ns = 128; while (__ldcg(C.seg_admitted + T.seg_id) == 0) { __nanosleep(ns); if (ns < 4096) ns <<= 1; } __threadfence(); }
+                }
                 __syncthreads();
             }
         }
-        const int rz = segmode ? G.r0 : 0;                                 // first antidiagonal computed
+        const int rz = segmode ? (repair ? G.r_begin - 1 : G.r0) : 0;      // first antidiagonal computed (repair: the last one of the predecessor, whose state is loaded)
         const int r_own = segmode ? G.r_begin : 0;                         // first antidiagonal whose results count
         if (tid == 0 && C.timeline && (!SEG || G.index == 0)) C.timeline[2 * T.orig] = global_ns();
         const int qlen = T.qlen, tlen = T.tlen, w = T.w;
@@ -306,7 +327,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
         const uint8_t* target = C.tarena + T.t_off;
         // traceback rows live in pool pages: row r is in page r / rows_per_page
         int tb_rip = SEG ? r_own % T.rows_per_page : 0, tb_pg = SEG ? r_own / T.rows_per_page : 0;     // row inside the current page, page number (a segmented task's pages are static: segments may share one)
-        uint8_t* tb_page = TB ? C.pool.base + (int64_t)table[tb_pg] * C.pool.page_bytes : nullptr;
+        uint8_t* tb_page = TB ? C.pool.base + (int64_t)(SEG ? __ldcg(table + tb_pg) : table[tb_pg]) * C.pool.page_bytes : nullptr;
         const int n_diag = qlen + tlen - 1;
 
         uint32_t U[8], V[8], X[8], Y[8], X2[8], Y2[8], S[8], Hr[8];
@@ -333,11 +354,37 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
         int32_t H0 = 0; int ap_t = 0;   // APPROX: score and column of the one cell that is followed (last_H0_t, :271-283); every thread keeps them
         int s3 = 0;                 // r % 3
 
+        if (SEG && repair) {
+            // the predecessor's state after its last antidiagonal (snapshot slot 2*(index-1)): registers, sequence windows, and the
+            // edge slots the first iteration reads; from here the run is the unsegmented one, in the predecessor's score frame
+            const uint32_t* mine = C.seg_snap + C.seg_tasks[T.seg_id].snap_off + (int64_t)(2 * (G.index - 1)) * SEG_SNAP_WORDS + SEG_SNAP_HDR + tid;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                U[k] = __ldcg(mine + (0 + k) * NT); V[k] = __ldcg(mine + (8 + k) * NT); X[k] = __ldcg(mine + (16 + k) * NT); Y[k] = __ldcg(mine + (24 + k) * NT);
+                X2[k] = __ldcg(mine + (32 + k) * NT); Y2[k] = __ldcg(mine + (40 + k) * NT); S[k] = __ldcg(mine + (48 + k) * NT); Hr[k] = __ldcg(mine + (56 + k) * NT);
+            }
+            Vt = (int)__ldcg(mine + 64 * NT); Hb = (int32_t)__ldcg(mine + 65 * NT); hprev_keep = (int32_t)__ldcg(mine + 66 * NT);
+            const int rp = G.r_begin - 1, nb = Vt << 4;
+            for (int c = 0; c < 16; ++c) {
+                const int t = nb + c, j = rp - t;
+                const uint32_t tbse = (t >= 0 && t < tlen) ? target[t] : 0, qbse = (j >= 0 && j < qlen) ? query[j] : 0;
+                tw |= (tbse & 3u) << (2 * c); qw |= (qbse & 3u) << (2 * c);
+                amb |= ((tbse > 3u ? 0x10000u : 0u) | (qbse > 3u ? 1u : 0u)) << c;
+            }
+            band_limits(rp, qlen, tlen, w, st0p, en0p);
+            if (NW > 1 && lane == 31) {
+                const uint32_t ea = sb + OFF_EDGE + (uint32_t)((rp & 1) * NW + warp) * 32u;
+                sts128(ea, make_uint4(X[7], V[7], DUAL ? X2[7] : 0u, qw));
+                sts32(ea + 16u, (uint32_t)(Hb + sext16(Hr[7] >> 16)));
+                sts32(ea + 20u, amb);
+            }
+            __syncthreads();
+        }
         // The antidiagonal loop exists twice, with and without the wildcard bookkeeping, chosen once per task:
         // left to itself the compiler predicates the `if (wild)` blocks, and predicated-off instructions still issue.
         auto fill_loop = [&](auto wild_c) {
         constexpr bool wild = decltype(wild_c)::value;
-        for (int r = rz;; ++r) {
+        for (int r = (SEG && repair) ? rz + 1 : rz;; ++r) {
             const int par = r & 1, ppar = par ^ 1;
             // a later segment of a task that z-dropped inside segment 0: stop through the same flag a z-drop uses (posted at
             // iteration r, seen by every thread in section (A) of iteration r+1)
@@ -734,7 +781,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                 }
                 if (TB && (!SEG || r >= r_own) && ++tb_rip == T.rows_per_page) {
                     tb_rip = 0; ++tb_pg;
-                    if (tb_pg < T.tb_pages) tb_page = C.pool.base + (int64_t)table[tb_pg] * C.pool.page_bytes;
+                    if (tb_pg < T.tb_pages) tb_page = C.pool.base + (int64_t)(SEG ? __ldcg(table + tb_pg) : table[tb_pg]) * C.pool.page_bytes;
                     // (thread 0 of a lazily growing task) one page ahead: the CTA reads table[tb_pg + 1] a whole page of antidiagonals from now
                     if (!SEG && tid == 0 && tb_pg + 1 < T.tb_pages) {
                         const int held = (int)lds32(sb + OFF_HELD);
@@ -757,8 +804,17 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
             __syncthreads();
             if (tid == 0) {
                 C.seg_foot[ST.first_seg + G.index] = stop_r < G.r_end ? stop_r : -1;      // the band ran out inside this segment
-                __threadfence();
-                sts32(sb + OFF_SEG, atomicAdd(&C.seg_done[T.seg_id], 1) == G.count - 1 ? 1u : 0u);
+                if (repair) {
+                    // this segment now continues its predecessor exactly: boundary index-1 holds by construction and the two share
+                    // one score frame (header word 2 of the snapshot the cold start had left at slot 2*(index-1)+1)
+                    uint32_t* hb = C.seg_snap + ST.snap_off + (int64_t)(2 * (G.index - 1) + 1) * SEG_SNAP_WORDS;
+                    hb[2] = 1u;
+                    __threadfence();
+                    sts32(sb + OFF_SEG, 1u);
+                } else {
+                    __threadfence();
+                    sts32(sb + OFF_SEG, atomicAdd(&C.seg_done[T.seg_id], 1) == G.count - 1 ? 1u : 0u);
+                }
             }
             __syncthreads();
             if (!lds32(sb + OFF_SEG)) continue;
@@ -835,7 +891,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                     if (stop) stop_seg = sgi;
                     if (!stop && sgi + 1 < G.count) {
                         const uint32_t* A = C.seg_snap + ST.snap_off + (int64_t)(2 * sgi) * SEG_SNAP_WORDS;
-                        delta += (int32_t)__ldcg(A) - (int32_t)__ldcg(A + SEG_SNAP_WORDS);
+                        if (__ldcg(A + SEG_SNAP_WORDS + 2) == 0u) delta += (int32_t)__ldcg(A) - (int32_t)__ldcg(A + SEG_SNAP_WORDS);      // (a repaired segment keeps its predecessor's frame)
                     }
                 }
                 if (lane == 0) sts32(sb + OFF_SEG, (uint32_t)stop_seg);
@@ -843,69 +899,48 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
             __syncthreads();
             const int n_bound = (int)lds32(sb + OFF_SEG);      // boundaries 0 .. n_bound-1 carry the result
             __syncthreads();
-            // (2) those boundaries: the state segment b+1 reached from its cold start == the state segment b reached
-            bool bad = false;
+            // (2) those boundaries, in order: the state segment b+1 reached from its cold start == the state segment b reached.
+            // The first one that does not hold is repaired (its upper segment runs again from the true state, on this CTA),
+            // then everything is looked at again: the records above it were in the wrong frame, so the replay may end elsewhere.
+            int first_bad = -1;
             for (int b = 0; b < n_bound; ++b) {
                 if (((volatile int32_t*)C.seg_foot)[ST.first_seg + b] >= 0) break;       // the alignment ends inside segment b
+                const uint32_t* A = C.seg_snap + ST.snap_off + (int64_t)(2 * b) * SEG_SNAP_WORDS;
+                const uint32_t* B = A + SEG_SNAP_WORDS;
+                if (__ldcg(B + 2) != 0u) continue;                                         // repaired before: holds by construction
+                bool bad = false;
                 const int rb = C.segs[ST.first_seg + b].r_end - 1;
                 int st0b, en0b;
                 band_limits(rb, qlen, tlen, w, st0b, en0b);
                 const int stv = round_st(st0b) >> 4, env = round_en(en0b) >> 4;
-                const uint32_t* A = C.seg_snap + ST.snap_off + (int64_t)(2 * b) * SEG_SNAP_WORDS;
-                const uint32_t* B = A + SEG_SNAP_WORDS;
                 if (__ldcg(A + 1) != 1u || __ldcg(B + 1) != 1u) bad = true;
                 const int32_t ancA = (int32_t)__ldcg(A), ancB = (int32_t)__ldcg(B);
                 const uint32_t* a = A + SEG_SNAP_HDR + tid; const uint32_t* bq = B + SEG_SNAP_HDR + tid;
                 const int va = (int)__ldcg(a + 64 * NT), vb = (int)__ldcg(bq + 64 * NT);
                 if (va != vb) bad = true;
-#ifdef FSV_SEG_DEBUG
-                if (va != vb && tid < 4) printf("seg dbg: task %d boundary %d tid %d Vt %d vs %d (valid %u %u anc %d %d)\n", T.orig, b, tid, va, vb, __ldcg(A + 1), __ldcg(B + 1), ancA, ancB);
-#endif
-                if (va >= stv) for (int k = 48; k < 56; ++k) if (__ldcg(a + k * NT) != __ldcg(bq + k * NT)) {
-                    bad = true;     // s, also of vectors above the band
-#ifdef FSV_SEG_DEBUG
-                    printf("seg dbg: task %d boundary %d rb %d tid %d Vt %d (band vectors %d..%d) S word %d: %08x vs %08x\n", T.orig, b, rb, tid, va, stv, env, k - 48, __ldcg(a + k * NT), __ldcg(bq + k * NT));
-#endif
-                }
-#ifdef FSV_SEG_DEBUG
-                if (b == 0 && va - stv >= 92 && va - stv <= 99) {
-                    for (int arr = 0; arr < 7; ++arr)
-                        printf("dump idx %d arr %d A %08x %08x %08x %08x %08x %08x %08x %08x | B %08x %08x %08x %08x %08x %08x %08x %08x\n", va - stv, arr,
-                               __ldcg(a + (arr*8+0) * NT), __ldcg(a + (arr*8+1) * NT), __ldcg(a + (arr*8+2) * NT), __ldcg(a + (arr*8+3) * NT), __ldcg(a + (arr*8+4) * NT), __ldcg(a + (arr*8+5) * NT), __ldcg(a + (arr*8+6) * NT), __ldcg(a + (arr*8+7) * NT),
-                               __ldcg(bq + (arr*8+0) * NT), __ldcg(bq + (arr*8+1) * NT), __ldcg(bq + (arr*8+2) * NT), __ldcg(bq + (arr*8+3) * NT), __ldcg(bq + (arr*8+4) * NT), __ldcg(bq + (arr*8+5) * NT), __ldcg(bq + (arr*8+6) * NT), __ldcg(bq + (arr*8+7) * NT));
-                }
-#endif
+                if (va >= stv) for (int k = 48; k < 56; ++k) if (__ldcg(a + k * NT) != __ldcg(bq + k * NT)) bad = true;     // s, also of vectors above the band
                 if (va >= stv && va <= env) {
-                    for (int k = 0; k < 48; ++k) if (__ldcg(a + k * NT) != __ldcg(bq + k * NT)) {
-                        bad = true;             // u v x y x2 y2
-#ifdef FSV_SEG_DEBUG
-                        if (k % 8 == 0) printf("seg dbg: task %d boundary %d rb %d tid %d Vt %d (band %d..%d) array %d word %d: %08x vs %08x\n", T.orig, b, rb, tid, va, stv, env, k / 8, k % 8, __ldcg(a + k * NT), __ldcg(bq + k * NT));
-#endif
-                    }
+                    for (int k = 0; k < 48; ++k) if (__ldcg(a + k * NT) != __ldcg(bq + k * NT)) bad = true;             // u v x y x2 y2
                     const int32_t hba = (int32_t)__ldcg(a + 65 * NT), hbb = (int32_t)__ldcg(bq + 65 * NT);
                     for (int c = 0; c < 16; ++c) {                                                                   // H relative to the anchor lane
                         const int t = (va << 4) + c;
                         if (t < st0b || t > en0b) continue;
                         const uint32_t wa = __ldcg(a + (56 + (c & 7)) * NT), wb = __ldcg(bq + (56 + (c & 7)) * NT);
                         const int32_t ha = hba + sext16(c & 8 ? wa >> 16 : wa) - ancA, hb = hbb + sext16(c & 8 ? wb >> 16 : wb) - ancB;
-                        if (ha != hb) {
-                            bad = true;
-#ifdef FSV_SEG_DEBUG
-                            if (c == 0) printf("seg dbg: task %d boundary %d tid %d Vt %d lane %d H %d vs %d\n", T.orig, b, tid, va, c, ha, hb);
-#endif
-                        }
+                        if (ha != hb) bad = true;
                     }
                 }
+                if (__syncthreads_or(bad)) { first_bad = b; break; }
             }
-            if (__syncthreads_or(bad)) {         // re-run the task whole (this CTA, static pages)
-                if (tid == 0) atomicAdd(&C.seg_done[T.seg_id], 1 << 20);      // counted by the host (fsv_stats.segment_fallbacks)
-                seg_redo = ST.first_seg;
+            if (first_bad >= 0) {
+                if (tid == 0) atomicAdd(&C.seg_done[T.seg_id], 1 << 20);      // counted by the host (fsv_stats.segment_fallbacks = repaired segments)
+                seg_redo = ST.first_seg + first_bad + 1;
                 continue;
             }
             if (warp == 0) finish_task(C, T, table, e2, cells2, TB);
             __syncthreads();
             if (tid == 0) {
-                seg_release(C, T.seg_id);
+                seg_release(C, T, table);
                 if (C.timeline) C.timeline[2 * T.orig + 1] = global_ns();
             }
             continue;
@@ -917,7 +952,6 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
         if (tid == 0) {
             const bool lazy = C.pool.lazy && C.pool.lazy_min_pages > 0 && T.tb_pages >= C.pool.lazy_min_pages;      // as task_pages decided
             if (!SEG) pool_free(C.pool, (int)lds32(sb + OFF_HELD), table, lazy ? C.slot_base + (int)blockIdx.x : -1);
-            else seg_release(C, T.seg_id);                  // (re-run of a segmented task)
             if (C.timeline) C.timeline[2 * T.orig + 1] = global_ns();
         }
     }

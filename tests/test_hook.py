@@ -24,8 +24,12 @@ def _oracle_records(O, windows, contigs, preset="asm5"):
     for (chrom, start, t), (qn, q) in zip(windows, contigs):
         r, cig = O.extd2(q, t, sc, w=ksw_band(2000), zdrop=p.zdrop, flag=0)
         cg = hook.cigar_tuples(cig)
-        recs.append(hook.AlignedContig(qn, chrom, start, start + sum(n for op, n in cg if op in (0, 2)), cg, False, 60,
-                                       len(q), int(r["score"]), bool(r["zdropped"])))
+        ref_end = start + sum(n for op, n in cg if op in (0, 2))
+        q_used = sum(n for op, n in cg if op in (0, 1))
+        mapq = 60
+        if q_used < len(q):         # z-dropped: soft clip for the unaligned tail, mapq 0 (hook.records_from_results)
+            cg = cg + [(4, len(q) - q_used)]; mapq = 0
+        recs.append(hook.AlignedContig(qn, chrom, start, ref_end, cg, False, mapq, len(q), int(r["score"]), bool(r["zdropped"])))
     return recs
 
 
