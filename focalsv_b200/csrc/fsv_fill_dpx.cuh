@@ -36,6 +36,7 @@ constexpr int DPX_MAX_WARPS = 8;
 // holding (or rebuilding) fifteen registers.
 struct DpxK {
     uint32_t gU, gX, gY, gX2, gY2, sInit, sMch, sMis, sAmb, kClamp, kQ, kQ2, kQE, kQE2, kBias;
+    uint32_t kClamp1, kQp, kQ2p;      // kClamp | 0x0001, kQ | 0x0002, kQ2 | 0x0002 per half: see "a - b in two instructions" in dpx_cells
     int qe, qe2, bias, r0_bias;
 };
 
@@ -127,6 +128,7 @@ struct DpxConst : DpxK {
         sAmb = both((DUAL ? hi8(sc.sc_N) : hi8(sc.sc_N + 2 * qe)) | cS);      // either base is the wildcard m-1 (:68,130)
         kClamp = both(hi8(sc.max_sc_clamp));
         kQ = both(hi8(sc.q)); kQ2 = both(hi8(sc.q2)); kQE = both(hi8(qe)); kQE2 = both(hi8(qe2));
+        kClamp1 = kClamp | 0x00010001u; kQp = kQ | 0x00020002u; kQ2p = kQ2 | 0x00020002u;
         bias = DUAL ? 0 : qe; r0_bias = DUAL ? qe : 2 * qe;
         kBias = both((uint32_t)bias & 0xffffu);
     }
@@ -174,21 +176,27 @@ __device__ __forceinline__ void dpx_cells(uint32_t (&U)[8], uint32_t (&V)[8], ui
         uint32_t zc, code, a, b, a2 = 0, b2 = 0;
         a = __vadd2(xt1, vt1);
         b = __vadd2(Y[k], ut);
+        // a - b in two instructions.  __vsub2 costs three on sm_100a (LOP3 ~b, VIADD.16x2 +0x00010001, VIADD.16x2): there is no
+        // 16x2 subtract.  Every value here is an int8 in the HIGH byte of its half with a known LOW byte, so the "+1" of the two's
+        // complement can ride in the low bytes instead: with lo(p) + lo(~b) = 0x100 the carry into the high byte is that +1 and
+        // the low byte of the result is 0.  u, v, z have low byte 0, so z gets low byte 1 for z + ~v (1 + 0xff), and q gets low
+        // byte 2 for q + ~z (2 + 0xfe).
         if (DUAL) {
             a2 = __vadd2(x2t1, vt1);
             b2 = __vadd2(Y2[k], ut);
             const uint32_t zk = __vimax3_s16x2(__vimax3_s16x2(S[k], a, b), a2, b2);
             code = zk & 0x00070007u;
-            zc = __vmins2(zk & 0xff00ff00u, K.kClamp);
+            zc = __vmins2((zk & 0xff00ff00u) | 0x00010001u, K.kClamp1);
         } else {
             const uint32_t t1 = __vmaxs2(S[k], a);                 // signed (:179)
             const uint32_t t2 = __vmaxs2(t1, b);                   // d = b > z (signed compare, :180)
             code = t2 & 0x00070007u;
-            zc = __vminu2(__vmaxu2(t1 & 0xff00ff00u, b & 0xff00ff00u), K.kClamp);   // unsigned (:41-42)
+            zc = __vminu2(__vmaxu2((t1 & 0xff00ff00u) | 0x00010001u, (b & 0xff00ff00u) | 0x00010001u), K.kClamp1);   // unsigned (:41-42)
         }
-        U[k] = __vsub2(zc, vt1);
-        V[k] = __vsub2(zc, ut);
-        const uint32_t n1 = __vsub2(K.kQ, zc);
+        U[k] = __vadd2(zc, ~vt1);
+        V[k] = __vadd2(zc, ~ut);
+        const uint32_t nz = ~zc;
+        const uint32_t n1 = __vadd2(K.kQp, nz);
         uint32_t fl = 0;
         if (RIGHT) {
             // right alignment sets a continuation bit when the gap value is >= 0 BEFORE the max with 0 (:212-218),
