@@ -48,7 +48,10 @@ PAIR_DTYPE = np.dtype([("a_off", "<i8"), ("b_off", "<i8"), ("a_len", "<i4"), ("b
 RECORD_DTYPE = np.dtype([("pos", "<i8"), ("ref_end", "<i8"), ("cigar_off", "<i8"), ("n_cigar", "<i4"), ("query_length", "<i4"),
                          ("score", "<i4"), ("zdropped", "<i4"), ("is_reverse", "<i4"), ("mapq", "<i4")], align=True)
 PIECE_DTYPE = np.dtype([("q_beg", "<i4"), ("q_end", "<i4"), ("t_beg", "<i4"), ("t_end", "<i4")], align=True)
-assert RECORD_DTYPE.itemsize == 48 and PIECE_DTYPE.itemsize == 16
+CHAIN_DTYPE = np.dtype([("strand", "<i4"), ("score", "<i4"), ("n_anchors", "<i4"), ("sub_score", "<i4"), ("q_beg", "<i4"), ("q_end", "<i4"),
+                        ("t_beg", "<i4"), ("t_end", "<i4"), ("piece_off", "<i4"), ("n_pieces", "<i4"), ("lq", "<i4"), ("lt", "<i4"),
+                        ("rq", "<i4"), ("rt", "<i4")], align=True)
+assert RECORD_DTYPE.itemsize == 48 and PIECE_DTYPE.itemsize == 16 and CHAIN_DTYPE.itemsize == 56
 assert TASK_DTYPE.itemsize == 40 and RESULT_DTYPE.itemsize == 64 and SIGNATURE_DTYPE.itemsize == 32 and PAIR_DTYPE.itemsize == 24
 
 # fields that must be bit-identical to ksw_extz_t (ksw2.h:23-32)
@@ -58,6 +61,11 @@ EZ_FIELDS = ("max", "zdropped", "max_q", "max_t", "mqe", "mqe_t", "mte", "mte_q"
 class PresetC(C.Structure):
     _fields_ = [("name", C.c_char * 16)] + [(k, C.c_int32) for k in
                 ("a", "b", "q", "e", "q2", "e2", "zdrop", "zdrop_inv", "bw", "bw_long", "sc_ambi", "end_bonus")]
+
+
+class ChainOpts(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("k", "w", "max_occ", "max_gap", "min_fill", "max_chains", "min_chain_score", "min_anchors",
+                                         "a", "q", "e", "end_bonus")]
 
 
 class Stats(C.Structure):

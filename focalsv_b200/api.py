@@ -21,7 +21,7 @@ EXPORTS = ("fsv_init", "fsv_destroy", "fsv_strerror", "fsv_last_error", "fsv_abi
            "fsv_get_stats", "fsv_set_option", "fsv_align_batch", "fsv_batch_create", "fsv_batch_run",
            "fsv_batch_fetch", "fsv_batch_destroy", "fsv_ksw_extz2", "fsv_ksw_extd2", "fsv_task_cells",
            "fsv_lpt_bins", "fsv_measure_int_peak", "fsv_batch_timeline", "fsv_batch_signatures", "fsv_edit_distance_batch",
-           "fsv_preset_lookup", "fsv_realign_regions", "fsv_chain_pieces", "fsv_stitch_cigars", "fsv_batch_plan")
+           "fsv_preset_lookup", "fsv_realign_regions", "fsv_chain_pieces", "fsv_stitch_cigars", "fsv_batch_plan", "fsv_chain_pair")
 
 _lib = None
 
@@ -70,6 +70,7 @@ def load_library(path=None):
     lib.fsv_chain_pieces.argtypes = [vp, i32, vp, i32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, sz, C.POINTER(sz),
                                      C.POINTER(i32), C.POINTER(i32)]
     lib.fsv_stitch_cigars.argtypes = [vp, vp, sz, vp, vp, vp, sz, C.POINTER(sz)]
+    lib.fsv_chain_pair.argtypes = [vp, i32, vp, i32, C.POINTER(_abi.ChainOpts), vp, sz, C.POINTER(sz), vp, sz, C.POINTER(sz)]
     lib.fsv_preset_lookup.argtypes = [C.c_char_p, C.POINTER(_abi.PresetC), C.POINTER(Scoring)]
     lib.fsv_realign_regions.argtypes = [vp, vp, sz, vp, vp, vp, sz, vp, vp, sz, C.c_char_p, C.c_int, C.c_int, vp, vp, sz, C.POINTER(sz)]
     lib.fsv_task_cells.argtypes = [i32, i32, i32]
@@ -110,6 +111,25 @@ def chain_pieces(query, target, k=19, w=19, max_occ=50, max_gap=100000, min_fill
         if rc != 0:
             raise FsvError(rc, lib.fsv_strerror(rc).decode())
         return out[:n.value], sc.value, na.value
+
+
+def chain_pair(query, target, opts):
+    """fsv_chain_pair (host only): both strands, primary + supplementary chains, extension offers.
+    Returns (chains[CHAIN_DTYPE], pieces[PIECE_DTYPE])."""
+    lib = load_library()
+    q = np.ascontiguousarray(query, dtype=np.uint8); t = np.ascontiguousarray(target, dtype=np.uint8)
+    ccap, pcap = 8, 1024
+    while True:
+        ch = np.zeros(ccap, dtype=_abi.CHAIN_DTYPE); pc = np.zeros(pcap, dtype=_abi.PIECE_DTYPE)
+        nc = C.c_size_t(0); npc = C.c_size_t(0)
+        rc = lib.fsv_chain_pair(q.ctypes.data, q.size, t.ctypes.data, t.size, C.byref(opts), ch.ctypes.data, ccap, C.byref(nc),
+                                pc.ctypes.data, pcap, C.byref(npc))
+        if rc == _abi.ERR_CIGAR_CAP:
+            ccap, pcap = int(nc.value) + 4, int(npc.value) + 16
+            continue
+        if rc != 0:
+            raise FsvError(rc, lib.fsv_strerror(rc).decode())
+        return ch[:nc.value], pc[:npc.value]
 
 
 def stitch_cigars(pieces, task_of, res, cigar_arena):

@@ -283,6 +283,33 @@ int fsv_chain_pieces(const uint8_t* query, int32_t qlen, const uint8_t* target, 
                      int k, int w, int max_occ, int max_gap, int min_fill,
                      fsv_piece* pieces, size_t cap, size_t* n_pieces, int32_t* chain_score, int32_t* n_anchors);
 
+/* Second version (host only, PARITY UNPINNED like fsv_chain_pieces): both strands, several chains per pair, extension ends.
+ * chains[0] is the primary alignment; the others are supplementary (their query interval overlaps the accepted ones by less
+ * than half).  Coordinates of a chain with strand = 1 refer to the REVERSE COMPLEMENT of the query.  pieces[piece_off ..
+ * piece_off + n_pieces) tile the core [q_beg, q_end) x [t_beg, t_end) in order (global fills, as fsv_chain_pieces);
+ * lq / lt (rq / rt) are the query / target bases before (after) the core to offer to an extension task
+ * (FSV_EZ_EXTZ_ONLY; the left one on reversed sequences with FSV_EZ_RIGHT | FSV_EZ_REV_CIGAR), as mm_align1 does.
+ * sub_score = best score of a chain that was dropped as a secondary of this one (mapq).
+ * FSV_ERR_CIGAR_CAP with *n_chains / *n_pieces = entries needed when a buffer is too small. */
+typedef struct fsv_chain_opts {
+    int32_t k, w;             /* minimizer k-mer and window (asm5: 19, 19) */
+    int32_t max_occ;          /* seeds occurring more often in the target are dropped */
+    int32_t max_gap;          /* chaining / extension reach (the preset's bw_long for assemblies) */
+    int32_t min_fill;         /* min_ksw_len: anchors at least this far apart bound a fill (200) */
+    int32_t max_chains;       /* primary + supplementary alignments kept per pair */
+    int32_t min_chain_score, min_anchors;      /* minimap2 -m 40 -n 3 */
+    int32_t a, q, e, end_bonus;                /* match score, gap open / extend of the preset: size of the extension offers */
+} fsv_chain_opts;
+typedef struct fsv_chain {
+    int32_t strand, score, n_anchors, sub_score;
+    int32_t q_beg, q_end, t_beg, t_end;
+    int32_t piece_off, n_pieces;
+    int32_t lq, lt, rq, rt;
+} fsv_chain;
+int fsv_chain_pair(const uint8_t* query, int32_t qlen, const uint8_t* target, int32_t tlen, const fsv_chain_opts* opts,
+                   fsv_chain* chains, size_t chain_cap, size_t* n_chains,
+                   fsv_piece* pieces, size_t piece_cap, size_t* n_pieces);
+
 /* Stitch the CIGARs of one pair's pieces, in order, into one (host only): task_of[i] = index of piece i's task in `res`
  * (its CIGAR is copied) or -1 (a piece with an empty side: a pure I / D of the other side's length); neighbouring
  * operations of the same kind are merged.  FSV_ERR_CIGAR_CAP with *n_out = words needed when `cap` is too small. */

@@ -238,3 +238,85 @@ def test_device_signatures_empty_and_capacity(aligner):
         assert len(b.signatures(np.array([7], dtype=np.int64))) == 0      # identical sequences: no signature
     finally:
         b.close()
+
+
+def test_multi_aligner_gathers_in_task_order(oracle):
+    """In-process multi-device path: LPT bins over the devices, host gather in the caller's order.  Two oracle-backed
+    'devices' must give exactly what one gives (host logic only; on a GPU box the same class wraps api.Aligner(dev))."""
+    from util import OracleRunner
+    windows, contigs, _ = _regions(21, n=9, L=3000)
+    one = hook.realign_regions(OracleRunner(oracle), windows, contigs, preset="asm5", bw=500)
+    multi = hook.MultiAligner([OracleRunner(oracle, threads=2), OracleRunner(oracle, threads=2), OracleRunner(oracle, threads=2)])
+    three = hook.realign_regions(multi, windows, contigs, preset="asm5", bw=500)
+    assert one == three
+    assert hook.realign_regions(hook.MultiAligner([OracleRunner(oracle)]), windows[:2], contigs[:2], preset="asm5", bw=500) == one[:2]
+
+
+@pytest.mark.gpu
+def test_multi_aligner_on_the_visible_gpus(oracle):
+    from focalsv_b200 import api
+    n_dev = max(1, min(api.load_library().fsv_device_count(), 4))
+    windows, contigs, _ = _regions(22, n=7, L=6000)
+    want = _oracle_records(oracle, windows, contigs)
+    multi = hook.MultiAligner.on_devices(list(range(n_dev)) if n_dev > 1 else [0, 0])      # one GPU: two contexts on it
+    try:
+        assert hook.realign_regions(multi, windows, contigs, preset="asm5", bw=2000) == want
+    finally:
+        multi.close()
+
+
+def _mm2_cases(seed=31):
+    rng = np.random.default_rng(seed)
+    ref = synth.random_seq(rng, 70000)
+    q, svs = synth.plant_svs(rng, ref[5000:60000], 5, max_net=6000, max_len=5000)
+    q = synth.mutate(rng, q, 0.001, 0.0002, 0.0002)
+    inv = np.concatenate([q[:20000], (3 - q[20000:29000][::-1]).astype(np.uint8), q[29000:]])
+    windows = [("chr7", 2000000, ref)] * 3
+    contigs = [("ctg_fwd", q), ("ctg_rev", (3 - q[::-1]).astype(np.uint8)), ("ctg_inv", inv)]
+    return ref, q, svs, windows, contigs
+
+
+def _check_mm2_records(recs, ref, q, svs, windows, contigs):
+    from focalsv_b200 import dropin
+    by = {}
+    for r in recs:
+        by.setdefault(r.qname, []).append(r)
+    fwd, rev, inv = by["ctg_fwd"], by["ctg_rev"], by["ctg_inv"]
+    assert len(fwd) == 1 and len(rev) == 1 and fwd[0].flag == 0 and rev[0].flag == 16
+    # the reverse-complemented contig aligns to the same place with the same CIGAR; SEQ is given on the reference strand
+    assert (fwd[0].pos, fwd[0].cigar, fwd[0].tags["NM"]) == (rev[0].pos, rev[0].cigar, rev[0].tags["NM"]) and fwd[0].seq == rev[0].seq
+    assert fwd[0].mapq == 60 and abs(fwd[0].pos - (2000000 + 5000)) < 100 and abs(fwd[0].reference_end - (2000000 + 60000)) < 100
+    # every record is a valid SAM record: query-consuming operations add up to the contig, SEQ matches, NM re-computes
+    for r in recs:
+        qlen = len(dict(contigs)[r.qname])
+        assert sum(n for op, n in r.cigar if op in (0, 1, 4, 5)) == qlen
+        assert len(r.seq) == sum(n for op, n in r.cigar if op in (0, 1, 4))
+        assert r.cigar[0][0] != 2 and r.cigar[-1][0] != 2 and all(n > 0 for _, n in r.cigar)
+    # the planted SVs come out of the primary's CIGAR (extension ends: no spurious gap at the window's corners)
+    sigs = hook.signatures([hook.AlignedContig(fwd[0].qname, fwd[0].reference_name, fwd[0].pos, fwd[0].reference_end, fwd[0].cigar, False, 60, 0, 0, False)])
+    got = sorted((s.svtype, s.svlen) for s in sigs)
+    want = sorted((t, L) for _, t, L in svs if L >= 30)
+    assert len(got) == len(want) and all(a[0] == b[0] and abs(a[1] - b[1]) <= 12 for a, b in zip(sorted(got, key=lambda x: x[1]), sorted(want, key=lambda x: x[1])))
+    # the inversion: a primary, two supplementary records, the inverted piece on the other strand, SA tags naming each other
+    assert len(inv) == 3 and sorted(r.flag for r in inv) == [0, 2048, 2064]
+    mid = [r for r in inv if r.flag == 2064][0]
+    assert abs((mid.reference_end - mid.pos) - 9000) < 200 and all(r.has_tag("SA") and r.get_tag("SA").count(";") == 2 for r in inv)
+    spans = sorted((r.pos, r.reference_end) for r in inv)
+    assert all(spans[i][1] <= spans[i + 1][0] + 50 for i in range(2))           # the three pieces tile the locus
+
+
+def test_map_contigs_strand_split_extension_cpu(oracle):
+    """Row f2 second version on the oracle arm (host logic: chaining on both strands, hole splitting, extension ends, tags)."""
+    from util import OracleRunner
+    ref, q, svs, windows, contigs = _mm2_cases()
+    _check_mm2_records(hook.map_contigs(OracleRunner(oracle), windows, contigs, preset="asm5", bw=2000), ref, q, svs, windows, contigs)
+
+
+@pytest.mark.gpu
+def test_map_contigs_gpu_equals_oracle_arm(oracle, aligner):
+    from util import OracleRunner
+    ref, q, svs, windows, contigs = _mm2_cases(32)
+    want = hook.map_contigs(OracleRunner(oracle), windows, contigs, preset="asm5", bw=2000)
+    got = hook.map_contigs(aligner, windows, contigs, preset="asm5", bw=2000)
+    assert [r.to_sam() for r in got] == [r.to_sam() for r in want]
+    _check_mm2_records(got, ref, q, svs, windows, contigs)
