@@ -103,6 +103,7 @@ __device__ int bt_walk(const TbPool& pool, const int32_t* table, const DevTask& 
         if (ended) {
             if (!valid_n) break;             // walked off the matrix
             state = ns_n;
+            if (state > 4) break;            // (not a ksw2 state: only a corrupted traceback row could hold it; never loop on it)
             emit(op_of(state), 1);
             if (state == 0) { --i; --j; }
             else if (state == 1 || state == 3) --i;

@@ -9,6 +9,7 @@
 // There is no CPU path in this file: every result is produced by the CUDA kernels in
 // fsv_fill_exact.cuh / fsv_fill_dpx.cuh / fsv_backtrack.cuh.
 #include <algorithm>
+#include <functional>
 #include <cstdio>
 #include <thread>
 #include <cstdlib>
@@ -58,7 +59,7 @@ struct fsv_ctx {
                                      // those whose chain of antidiagonals would outlast 60 % of the batch's throughput time)
     int segment_warm_pct = 400;      // cold-start lead of a segment, in percent of the band width (+1024 antidiagonals)
     int segment_align_pages = 0;     // 0 = segments are multiples of 1024 antidiagonals (default), 1 = whole traceback pages
-    int segment_auto_pct = 35;       // auto mode: tasks whose chain of antidiagonals outlasts this share of the batch's throughput time are segmented
+    int segment_auto_pct = 70;       // auto mode: tasks whose chain of antidiagonals outlasts this share of the batch's estimated time are segmented
     int segment_extz = 1;            // auto mode: 1 = extension (EXTZ_ONLY) tasks are segmented too, 0 = global tasks only
     int64_t segment_rows = 0;        // target antidiagonals per segment, rounded up to 1024 (0 = auto: 4 x or 2 x the warm-up)
     int lazy_min_pages = 16;    // DPX tasks with at least this many traceback pages take them as they advance (0 = all up front)
@@ -517,24 +518,65 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
     // a segment costs warm / seg_rows extra cells, a whole task that starts late keeps one CTA busy after the batch has ended.
     std::vector<uint8_t> is_seg(n, 0);
     if (c->segment_min_diags != 0) {
-        // auto: the batch's throughput time if every SM were full (SM-seconds model of the exclusive planning below); a task whose
-        // own chain would outlast `segment_auto_pct` % of it (or of 20 ms) is cut up
+        // auto: a task is worth cutting up when its own chain of antidiagonals is long against the time the batch takes anyway.
+        // That time is estimated per warp class with the SM-seconds model of the exclusive planning below: longest-first list
+        // scheduling of the whole tasks on the class's CTA slots (so a uniform batch of a few waves is seen for what it is),
+        // the work of the tasks already chosen spread over all slots.  Going down the eligible tasks by length, task i is
+        // segmented while  chain_i > segment_auto_pct % of that estimate.
         int64_t min_diags = c->segment_min_diags;
+        auto t_diag = [](int nw) { return nw <= 2 ? 2.0e-6 : nw == 4 ? 1.8e-6 : 1.55e-6; };
+        auto occ_of = [](int nw) { return nw == 1 ? 12 : nw == 2 ? 6 : nw == 4 ? 3 : 2; };
         double W = 0;
-        for (size_t i = 0; i < n; ++i) if (b->is_dpx[i]) {
-            const int nw = b->tasks[i].nw;
-            W += (double)(b->tasks[i].qlen + b->tasks[i].tlen) * (nw <= 2 ? 2.0e-6 : nw == 4 ? 1.8e-6 : 1.55e-6) / (nw == 1 ? 12.0 : nw == 2 ? 6.0 : nw == 4 ? 3.0 : 2.0);
-        }
+        for (size_t i = 0; i < n; ++i) if (b->is_dpx[i]) W += (double)(b->tasks[i].qlen + b->tasks[i].tlen) * t_diag(b->tasks[i].nw) / occ_of(b->tasks[i].nw);
         const double t_thr = std::max(W / c->sm_count, 0.020);
-        if (min_diags < 0) min_diags = (int64_t)(c->segment_auto_pct * 0.01 * t_thr / 1.55e-6);
-        std::vector<int32_t> by_len;
-        for (size_t i = 0; i < n; ++i) {
+        auto eligible = [&](size_t i) {
             const DevTask& d = b->tasks[i];
-            if (b->is_dpx[i] && d.tb_pages > 0 && !(d.flag & (FSV_EZ_RIGHT | FSV_EZ_SCORE_ONLY | FSV_EZ_APPROX_MAX)) && d.w >= 64 &&
-                (int64_t)d.qlen + d.tlen - 1 >= min_diags && d.tb_pages <= b->pool_pages &&
-                !(c->segment_min_diags < 0 && !c->segment_extz && (d.flag & FSV_EZ_EXTZ_ONLY)))
-                by_len.push_back((int32_t)i);
+            return b->is_dpx[i] && d.tb_pages > 0 && !(d.flag & (FSV_EZ_RIGHT | FSV_EZ_SCORE_ONLY | FSV_EZ_APPROX_MAX)) && d.w >= 64 &&
+                   d.tb_pages <= b->pool_pages && !(c->segment_min_diags < 0 && !c->segment_extz && (d.flag & FSV_EZ_EXTZ_ONLY));
+        };
+        std::vector<uint8_t> chosen(n, 0);
+        if (min_diags < 0) {
+            for (int nw : {8, 6, 4, 2, 1}) {
+                std::vector<int32_t> cls;
+                for (size_t i = 0; i < n; ++i) if (b->is_dpx[i] && b->tasks[i].nw == nw) cls.push_back((int32_t)i);
+                if (cls.empty()) continue;
+                std::stable_sort(cls.begin(), cls.end(), [&](int32_t a, int32_t x) { return b->tasks[a].qlen + b->tasks[a].tlen > b->tasks[x].qlen + b->tasks[x].tlen; });
+                const int slots = c->sm_count * occ_of(nw);
+                const double td = t_diag(nw);
+                auto chain = [&](int32_t ti) { return (double)(b->tasks[(size_t)ti].qlen + b->tasks[(size_t)ti].tlen) * td; };
+                double w_seg = 0;                    // slot-seconds of the tasks chosen so far, warm-up overhead included
+                auto makespan = [&]() {
+                    // list scheduling of the whole tasks (longest first) behind the divisible work of the chosen ones
+                    std::vector<double> heap((size_t)slots, std::max(w_seg / slots, 0.0));
+                    double m = heap[0];
+                    const bool few_waves = cls.size() <= (size_t)8 * slots;
+                    double w_whole = 0;
+                    for (int32_t ti : cls) if (!chosen[(size_t)ti]) {
+                        const double cch = chain(ti);
+                        w_whole += cch;
+                        if (!few_waves) { m = std::max(m, cch); continue; }
+                        std::pop_heap(heap.begin(), heap.end(), std::greater<double>());
+                        heap.back() += cch; m = std::max(m, heap.back());
+                        std::push_heap(heap.begin(), heap.end(), std::greater<double>());
+                    }
+                    return std::max(std::max(m, (w_seg + w_whole) / slots), 0.020);
+                };
+                double M = makespan();
+                int since = 0;
+                for (int32_t ti : cls) {
+                    if (!eligible((size_t)ti)) continue;
+                    if (chain(ti) <= c->segment_auto_pct * 0.01 * M) break;
+                    chosen[(size_t)ti] = 1;
+                    const DevTask& d = b->tasks[(size_t)ti];
+                    const double warm = (double)c->segment_warm_pct * d.w / 100 + 1024, rows = std::max(4.0 * warm, 16384.0);
+                    w_seg += chain(ti) * (1.0 + warm / rows);
+                    if (++since >= 8 || cls.size() <= 64) { M = makespan(); since = 0; }
+                }
+            }
         }
+        std::vector<int32_t> by_len;
+        for (size_t i = 0; i < n; ++i)
+            if (eligible(i) && (min_diags < 0 ? chosen[i] != 0 : (int64_t)b->tasks[i].qlen + b->tasks[i].tlen - 1 >= min_diags)) by_len.push_back((int32_t)i);
         std::stable_sort(by_len.begin(), by_len.end(), [&](int32_t a, int32_t x) { return b->tasks[a].qlen + b->tasks[a].tlen > b->tasks[x].qlen + b->tasks[x].tlen; });
         std::vector<std::vector<int32_t>> per_nw(9);
         struct SegPlan { int32_t ti; int64_t seg_rows, warm; int n_segs; };
@@ -559,8 +601,8 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
             if (c->segment_rows > 0 || total_segs >= c->sm_count) break;
         }
         if (getenv("FSV_TRACE"))
-            fprintf(stderr, "[fsv] segment plan: throughput time %.3f s, min_diags %lld, eligible %zu -> %zu tasks in %d segments\n",
-                    t_thr, (long long)min_diags, by_len.size(), plan.size(), total_segs);
+            fprintf(stderr, "[fsv] segment plan: throughput time %.3f s, %s, chosen %zu -> %zu tasks in %d segments\n",
+                    t_thr, min_diags < 0 ? "auto" : "fixed threshold", by_len.size(), plan.size(), total_segs);
         std::vector<int> n_in_class(9, 0);
         for (const SegPlan& sp : plan) {
             const int32_t ti = sp.ti;

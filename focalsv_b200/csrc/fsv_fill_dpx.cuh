@@ -37,6 +37,7 @@ constexpr int DPX_MAX_WARPS = 8;
 struct DpxK {
     uint32_t gU, gX, gY, gX2, gY2, sInit, sMch, sMis, sAmb, kClamp, kQ, kQ2, kQE, kQE2, kBias;
     uint32_t kClamp1, kQp, kQ2p;      // kClamp | 0x0001, kQ | 0x0002, kQ2 | 0x0002 per half: see "a - b in two instructions" in dpx_cells
+    uint32_t nQE, nQE2, nBias;        // -(q+e), -(q2+e2), -bias per half: x - const is x + (-const), one VIADD.16x2
     int qe, qe2, bias, r0_bias;
 };
 
@@ -129,8 +130,9 @@ struct DpxConst : DpxK {
         kClamp = both(hi8(sc.max_sc_clamp));
         kQ = both(hi8(sc.q)); kQ2 = both(hi8(sc.q2)); kQE = both(hi8(qe)); kQE2 = both(hi8(qe2));
         kClamp1 = kClamp | 0x00010001u; kQp = kQ | 0x00020002u; kQ2p = kQ2 | 0x00020002u;
+        nQE = both(hi8(-qe)); nQE2 = both(hi8(-qe2));
         bias = DUAL ? 0 : qe; r0_bias = DUAL ? qe : 2 * qe;
-        kBias = both((uint32_t)bias & 0xffffu);
+        kBias = both((uint32_t)bias & 0xffffu); nBias = both((uint32_t)(-bias) & 0xffffu);
     }
 };
 
@@ -205,20 +207,20 @@ __device__ __forceinline__ void dpx_cells(uint32_t (&U)[8], uint32_t (&V)[8], ui
             const uint32_t xa = __vmaxs2(pe, fE), ya = __vmaxs2(pf, fF);
             fl = ((~pe >> 12) & 0x00080008u) | ((~pf >> 11) & 0x00100010u);
             if (DUAL) {
-                const uint32_t n2 = __vsub2(K.kQ2, zc);
+                const uint32_t n2 = __vadd2(K.kQ2p, nz);
                 const uint32_t pe2 = __vadd2(a2, n2), pf2 = __vadd2(b2, n2);
                 const uint32_t xa2 = __vmaxs2(pe2, fE2), ya2 = __vmaxs2(pf2, fF2);
-                X[k] = __vsub2(xa, K.kQE); Y[k] = __vsub2(ya, K.kQE);
-                X2[k] = __vsub2(xa2, K.kQE2); Y2[k] = __vsub2(ya2, K.kQE2);
+                X[k] = __vadd2(xa, K.nQE); Y[k] = __vadd2(ya, K.nQE);
+                X2[k] = __vadd2(xa2, K.nQE2); Y2[k] = __vadd2(ya2, K.nQE2);
                 fl |= ((~pe2 >> 10) & 0x00200020u) | ((~pf2 >> 9) & 0x00400040u);
             } else { X[k] = xa; Y[k] = ya; }
         } else {
             const uint32_t xa = __viaddmax_s16x2(a, n1, fE), ya = __viaddmax_s16x2(b, n1, fF);
             if (DUAL) {
-                const uint32_t n2 = __vsub2(K.kQ2, zc);
+                const uint32_t n2 = __vadd2(K.kQ2p, nz);
                 const uint32_t xa2 = __viaddmax_s16x2(a2, n2, fE2), ya2 = __viaddmax_s16x2(b2, n2, fF2);
-                X[k] = __vsub2(xa, K.kQE); Y[k] = __vsub2(ya, K.kQE);
-                X2[k] = __vsub2(xa2, K.kQE2); Y2[k] = __vsub2(ya2, K.kQE2);
+                X[k] = __vadd2(xa, K.nQE); Y[k] = __vadd2(ya, K.nQE);
+                X2[k] = __vadd2(xa2, K.nQE2); Y2[k] = __vadd2(ya2, K.nQE2);
                 if (TB) fl = __vmins2(xa, oE) + __vmins2(ya, oF) + __vmins2(xa2, oE2) + __vmins2(ya2, oF2);
             } else {
                 X[k] = xa; Y[k] = ya;
@@ -245,14 +247,27 @@ __device__ __forceinline__ void seg_release(const RunCtx& C, const DevTask& T, c
     pool_free(C.pool, T.tb_pages, table);
 }
 
+// Spin until *flag == want (one thread).  Traps (the launch fails, nothing hangs) after twice the pool's stall limit: every
+// wait of this kind ends when an earlier task's CIGAR is written, which takes a fraction of a second.
+static __device__ __noinline__ void seg_spin(const int32_t* flag, int32_t want, int stall_ms, const char* what)
+{
+    unsigned ns = 128;
+    const long long t0 = global_ns();
+    while (__ldcg(flag) != want) {
+        __nanosleep(ns);
+        if (ns < 4096) ns <<= 1;
+        else if (global_ns() - t0 > 2ll * stall_ms * 1000000ll) { printf("fsv segment stall: block %d waits for %s %d, sees %d\n", (int)blockIdx.x, what, want, __ldcg(flag)); __trap(); }
+    }
+    __threadfence();
+}
+
 // A segmented task takes ALL its traceback pages at once when its first segment starts (thread 0 of that CTA), in the order of
 // the segment queue (tickets): a task either holds everything it needs or nothing, so the segments of the tasks in flight can
 // always finish.  While it waits it holds a reserve that keeps NEW ordinary tasks from starting (running ones still grow).
 static __device__ __noinline__ void seg_admit(const RunCtx& C, const DevTask& T, const SegTask& ST, int32_t* table, int32_t* ticket)
 {
     StallWatch watch;
-    unsigned ns = 128;
-    while (*(volatile int32_t*)ticket != ST.ticket) { __nanosleep(ns); if (ns < 4096) ns <<= 1; }
+    seg_spin(ticket, ST.ticket, C.pool.stall_ms, "ticket");
     for (;;) {
         atomicMax(C.pool.reserve, T.tb_pages);
         if (pool_try_alloc(C.pool, T.tb_pages, table, true)) break;
@@ -322,7 +337,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
             if (!repair) {
                 if (tid == 0) {
                     if (G.index == 0) seg_admit(C, T, STa, table, C.seg_ticket + P.seg_launch);
-                    else { unsigned ns = 128; while (__ldcg(C.seg_admitted + T.seg_id) == 0) { __nanosleep(ns); if (ns < 4096) ns <<= 1; } __threadfence(); }
+                    else seg_spin(C.seg_admitted + T.seg_id, 1, C.pool.stall_ms, "admission");
                 }
                 __syncthreads();
             }
@@ -573,7 +588,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {            // H[t] += v[t] - qe (:239-241)
                         uint32_t dv = prmt(V[k], 0u, extSel);
-                        if (!DUAL) dv = __vsub2(dv, K.kBias);
+                        if (!DUAL) dv = __vadd2(dv, K.nBias);
                         Hr[k] = __vadd2(Hr[k], dv);
                     }
                     const uint32_t pm = __vimax3_s16x2(__vimax3_s16x2(Hr[0], Hr[1], Hr[2]), __vimax3_s16x2(Hr[3], Hr[4], Hr[5]), __vmaxs2(Hr[6], Hr[7]));
@@ -702,7 +717,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             uint32_t dv = prmt(V[k], 0u, extSel);
-                            if (!DUAL) dv = __vsub2(dv, K.kBias);
+                            if (!DUAL) dv = __vadd2(dv, K.nBias);
                             Hr[k] = __vadd2(Hr[k], dv);
                         }
                         {   // lane en0 takes the value derived from its left neighbour; a vector whose lane 0 is en0
