@@ -562,15 +562,15 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
                     return std::max(std::max(m, (w_seg + w_whole) / slots), 0.020);
                 };
                 double M = makespan();
-                int since = 0;
+                int n_chosen = 0;
                 for (int32_t ti : cls) {
                     if (!eligible((size_t)ti)) continue;
-                    if (chain(ti) <= c->segment_auto_pct * 0.01 * M) break;
-                    chosen[(size_t)ti] = 1;
+                    if (chain(ti) <= c->segment_auto_pct * 0.01 * M || n_chosen >= 2048) break;
+                    chosen[(size_t)ti] = 1; ++n_chosen;
                     const DevTask& d = b->tasks[(size_t)ti];
                     const double warm = (double)c->segment_warm_pct * d.w / 100 + 1024, rows = std::max(4.0 * warm, 16384.0);
                     w_seg += chain(ti) * (1.0 + warm / rows);
-                    if (++since >= 8 || cls.size() <= 64) { M = makespan(); since = 0; }
+                    M = makespan();               // the estimate falls as the longest chains turn into divisible work
                 }
             }
         }

@@ -195,10 +195,20 @@ __device__ __forceinline__ void dpx_cells(uint32_t (&U)[8], uint32_t (&V)[8], ui
             code = t2 & 0x00070007u;
             zc = __vminu2(__vmaxu2((t1 & 0xff00ff00u) | 0x00010001u, (b & 0xff00ff00u) | 0x00010001u), K.kClamp1);   // unsigned (:41-42)
         }
+#ifdef FSV_OLD_SUB      // experiment: the three-instruction __vsub2 forms (zc then carries a low byte of 1 that must be masked away)
+        zc &= 0xff00ff00u;
+        U[k] = __vsub2(zc, vt1);
+        V[k] = __vsub2(zc, ut);
+        const uint32_t nz = __vsub2(0u, zc);      // -zc
+        const uint32_t n1 = __vadd2(K.kQ, nz);
+        const uint32_t kq2 = K.kQ2;
+#else
         U[k] = __vadd2(zc, ~vt1);
         V[k] = __vadd2(zc, ~ut);
         const uint32_t nz = ~zc;
         const uint32_t n1 = __vadd2(K.kQp, nz);
+        const uint32_t kq2 = K.kQ2p;
+#endif
         uint32_t fl = 0;
         if (RIGHT) {
             // right alignment sets a continuation bit when the gap value is >= 0 BEFORE the max with 0 (:212-218),
@@ -207,7 +217,7 @@ __device__ __forceinline__ void dpx_cells(uint32_t (&U)[8], uint32_t (&V)[8], ui
             const uint32_t xa = __vmaxs2(pe, fE), ya = __vmaxs2(pf, fF);
             fl = ((~pe >> 12) & 0x00080008u) | ((~pf >> 11) & 0x00100010u);
             if (DUAL) {
-                const uint32_t n2 = __vadd2(K.kQ2p, nz);
+                const uint32_t n2 = __vadd2(kq2, nz);
                 const uint32_t pe2 = __vadd2(a2, n2), pf2 = __vadd2(b2, n2);
                 const uint32_t xa2 = __vmaxs2(pe2, fE2), ya2 = __vmaxs2(pf2, fF2);
                 X[k] = __vadd2(xa, K.nQE); Y[k] = __vadd2(ya, K.nQE);
@@ -217,7 +227,7 @@ __device__ __forceinline__ void dpx_cells(uint32_t (&U)[8], uint32_t (&V)[8], ui
         } else {
             const uint32_t xa = __viaddmax_s16x2(a, n1, fE), ya = __viaddmax_s16x2(b, n1, fF);
             if (DUAL) {
-                const uint32_t n2 = __vadd2(K.kQ2p, nz);
+                const uint32_t n2 = __vadd2(kq2, nz);
                 const uint32_t xa2 = __viaddmax_s16x2(a2, n2, fE2), ya2 = __viaddmax_s16x2(b2, n2, fF2);
                 X[k] = __vadd2(xa, K.nQE); Y[k] = __vadd2(ya, K.nQE);
                 X2[k] = __vadd2(xa2, K.nQE2); Y2[k] = __vadd2(ya2, K.nQE2);
@@ -856,13 +866,16 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                     const DevSeg Gs = C.segs[ST.first_seg + sgi];
                     const int foot = ((volatile int32_t*)C.seg_foot)[ST.first_seg + sgi];
                     const int end = foot >= 0 ? foot : Gs.r_end;
+                    int4 rec_next = make_int4(0, 0, 0, 0);
+                    if (Gs.r_begin + lane < end) rec_next = __ldcg(C.seg_rec + ST.rec_off + Gs.r_begin + lane);
                     for (int d0 = Gs.r_begin; d0 < end && !stop; d0 += 32) {
                         // one record per lane; ksw_apply_zdrop's running maximum (ksw2.h:160-176: a later record wins only if
                         // strictly greater) is an inclusive warp scan with the state so far as the earliest element, every lane
-                        // tests its own record against the maximum BEFORE it, and the first lane that drops ends the replay
+                        // tests its own record against the maximum BEFORE it, and the first lane that drops ends the replay.
+                        // (the records of the next step are fetched while this one is scanned: the loop is one dependent load long otherwise)
                         const bool valid = d0 + lane < end;
-                        int4 rec = make_int4(0, 0, 0, 0);
-                        if (valid) rec = __ldcg(C.seg_rec + ST.rec_off + d0 + lane);
+                        const int4 rec = rec_next;
+                        if (d0 + 32 + lane < end) rec_next = __ldcg(C.seg_rec + ST.rec_off + d0 + 32 + lane);
                         const int d = d0 + lane;
                         int st0d, en0d;
                         band_limits(valid ? d : 0, qlen, tlen, w, st0d, en0d);

@@ -300,7 +300,7 @@ def _check_mm2_records(recs, ref, q, svs, windows, contigs):
     # the inversion: a primary, two supplementary records, the inverted piece on the other strand, SA tags naming each other
     assert len(inv) == 3 and sorted(r.flag for r in inv) == [0, 2048, 2064]
     mid = [r for r in inv if r.flag == 2064][0]
-    assert abs((mid.reference_end - mid.pos) - 9000) < 200 and all(r.has_tag("SA") and r.get_tag("SA").count(";") == 2 for r in inv)
+    assert abs((mid.reference_end - mid.pos) - 9000) < 800 and all(r.has_tag("SA") and r.get_tag("SA").count(";") == 2 for r in inv)
     spans = sorted((r.pos, r.reference_end) for r in inv)
     assert all(spans[i][1] <= spans[i + 1][0] + 50 for i in range(2))           # the three pieces tile the locus
 
