@@ -387,11 +387,11 @@ def main():
     try:
         if WORKLOAD != "cfg2":
             raise KeyError("the committed capture is of cfg2")
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r2.json")) as fh:
             tj = json.load(fh)
         traffic = {"dram_bytes_per_step": tj["dram_bytes_per_step"] * (cells_step / tj["cells_per_step"]),
                    "algorithmic_bytes_per_step": float(cells_step), "unit": "bytes (1 B traceback per in-band cell)",
-                   "source": "profiles/ncu_traffic_r1.json (ncu dram__bytes_read.sum + dram__bytes_write.sum of the fill launches)"}
+                   "source": "profiles/ncu_traffic_r2.json (ncu dram__bytes_read.sum + dram__bytes_write.sum of the fill launches of one step, round-2 build: " + ", ".join(sorted(tj["launches"])) + ")"}
     except Exception:
         pass
     roofline = {"bound": "int_alu", "kernel": "fsv_fill (DP fill incl. traceback store)",
