@@ -36,7 +36,7 @@ constexpr int DPX_MAX_WARPS = 8;
 // holding (or rebuilding) fifteen registers.
 struct DpxK {
     uint32_t gU, gX, gY, gX2, gY2, sInit, sMch, sMis, sAmb, kClamp, kQ, kQ2, kQE, kQE2, kBias;
-    uint32_t kClamp1, kQp, kQ2p;      // kClamp | 0x0001, kQ | 0x0002, kQ2 | 0x0002 per half: see "a - b in two instructions" in dpx_cells
+    uint32_t nClamp, kQ1, kQ21;       // ~kClamp, kQ | 0x0001, kQ2 | 0x0001 per half: see "z is kept complemented" in dpx_cells
     uint32_t nQE, nQE2, nBias;        // -(q+e), -(q2+e2), -bias per half: x - const is x + (-const), one VIADD.16x2
     int qe, qe2, bias, r0_bias;
 };
@@ -129,7 +129,7 @@ struct DpxConst : DpxK {
         sAmb = both((DUAL ? hi8(sc.sc_N) : hi8(sc.sc_N + 2 * qe)) | cS);      // either base is the wildcard m-1 (:68,130)
         kClamp = both(hi8(sc.max_sc_clamp));
         kQ = both(hi8(sc.q)); kQ2 = both(hi8(sc.q2)); kQE = both(hi8(qe)); kQE2 = both(hi8(qe2));
-        kClamp1 = kClamp | 0x00010001u; kQp = kQ | 0x00020002u; kQ2p = kQ2 | 0x00020002u;
+        nClamp = ~kClamp; kQ1 = kQ | 0x00010001u; kQ21 = kQ2 | 0x00010001u;
         nQE = both(hi8(-qe)); nQE2 = both(hi8(-qe2));
         bias = DUAL ? 0 : qe; r0_bias = DUAL ? qe : 2 * qe;
         kBias = both((uint32_t)bias & 0xffffu); nBias = both((uint32_t)(-bias) & 0xffffu);
@@ -158,12 +158,24 @@ __device__ __forceinline__ void dpx_profile_amb(uint32_t (&sv)[8], uint32_t amb,
     for (int k = 0; k < 8; ++k) { const uint32_t lm = prmt(bits << (7 - k), 0u, 0x9988u); sv[k] = (K.sAmb & lm) | (sv[k] & ~lm); }
 }
 
+// ~x as x * -1 + -1: an IMAD (FMA pipe) instead of a LOP3 (ALU pipe).  m1 = 0xffffffff in a register the compiler cannot see through.
+__device__ __forceinline__ uint32_t not_fma(uint32_t x, uint32_t m1)
+{
+#ifdef FSV_NOT_LOP3      // experiment: plain complement
+    (void)m1; return ~x;
+#else
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %2;" : "=r"(d) : "r"(x), "r"(m1));
+    return d;
+#endif
+}
+
 // The recurrence on the 16 lanes of one vector (:26-47, :171-196), words 7..0 so that word k-1 is
 // still "old" when word k reads it.  XT0/VT0/X2T0 are the t-1 operands of word 0.
 template <bool DUAL, bool TB, bool RIGHT>
 __device__ __forceinline__ void dpx_cells(uint32_t (&U)[8], uint32_t (&V)[8], uint32_t (&X)[8], uint32_t (&Y)[8],
                                           uint32_t (&X2)[8], uint32_t (&Y2)[8], const uint32_t (&S)[8],
-                                          uint32_t XT0, uint32_t VT0, uint32_t X2T0, const DpxK& K, uint4& tbo)
+                                          uint32_t XT0, uint32_t VT0, uint32_t X2T0, const DpxK& K, uint32_t ALL1, uint4& tbo)
 {
     using C = DpxConst<DUAL, RIGHT>;
     const uint32_t fE = both(C::cE), fF = both(C::cF), fE2 = both(C::cE2), fF2 = both(C::cF2);      // max(.,0) floors
@@ -175,40 +187,32 @@ __device__ __forceinline__ void dpx_cells(uint32_t (&U)[8], uint32_t (&V)[8], ui
     for (int k = 7; k >= 0; --k) {
         const uint32_t xt1 = k ? X[k - 1] : XT0, vt1 = k ? V[k - 1] : VT0, x2t1 = DUAL ? (k ? X2[k - 1] : X2T0) : 0;
         const uint32_t ut = U[k];
-        uint32_t zc, code, a, b, a2 = 0, b2 = 0;
+        uint32_t nz, a, b, a2 = 0, b2 = 0;
         a = __vadd2(xt1, vt1);
         b = __vadd2(Y[k], ut);
-        // a - b in two instructions.  __vsub2 costs three on sm_100a (LOP3 ~b, VIADD.16x2 +0x00010001, VIADD.16x2): there is no
-        // 16x2 subtract.  Every value here is an int8 in the HIGH byte of its half with a known LOW byte, so the "+1" of the two's
-        // complement can ride in the low bytes instead: with lo(p) + lo(~b) = 0x100 the carry into the high byte is that +1 and
-        // the low byte of the result is 0.  u, v, z have low byte 0, so z gets low byte 1 for z + ~v (1 + 0xff), and q gets low
-        // byte 2 for q + ~z (2 + 0xfe).
+        // z is kept COMPLEMENTED.  There is no 16x2 subtract on sm_100a (__vsub2 costs three instructions: LOP3 ~b, VIADD.16x2
+        // +0x00010001, VIADD.16x2), but every value here is an int8 in the HIGH byte of its half with a known LOW byte, and ~ turns
+        // min into max.  With nz = ~z carrying a low byte of 0xff (one LOP3: ~zk | 0x00ff00ff, which also drops the tie-break code):
+        //   clamp:  ~min(z, c) = max(~z, ~c)                                  (signed and unsigned alike)
+        //   u = z - v[t-1] = ~(nz + v[t-1]),  v = z - u = ~(nz + u)           (low bytes 0xff + 0 -> 0xff, no carry; ~ -> 0)
+        //   q - z = (q | 1) + nz                                              (low bytes 1 + 0xff: the carry is the +1 of the two's complement)
+        // and the two remaining complements are x * -1 + -1 on the FMA pipe (IMAD), which the ALU-heavy mix of this loop leaves idle:
+        // 8 instructions per word for clamp, u, v, q - z, q2 - z instead of 10 (13 with __vsub2).
+        uint32_t zk;
         if (DUAL) {
             a2 = __vadd2(x2t1, vt1);
             b2 = __vadd2(Y2[k], ut);
-            const uint32_t zk = __vimax3_s16x2(__vimax3_s16x2(S[k], a, b), a2, b2);
-            code = zk & 0x00070007u;
-            zc = __vmins2((zk & 0xff00ff00u) | 0x00010001u, K.kClamp1);
+            zk = __vimax3_s16x2(__vimax3_s16x2(S[k], a, b), a2, b2);
+            nz = __vmaxs2(~zk | 0x00ff00ffu, K.nClamp);
         } else {
             const uint32_t t1 = __vmaxs2(S[k], a);                 // signed (:179)
-            const uint32_t t2 = __vmaxs2(t1, b);                   // d = b > z (signed compare, :180)
-            code = t2 & 0x00070007u;
-            zc = __vminu2(__vmaxu2((t1 & 0xff00ff00u) | 0x00010001u, (b & 0xff00ff00u) | 0x00010001u), K.kClamp1);   // unsigned (:41-42)
+            zk = __vmaxs2(t1, b);                                  // d = b > z (signed compare, :180)
+            nz = __vmaxu2(__vminu2(~t1 | 0x00ff00ffu, ~b | 0x00ff00ffu), K.nClamp);   // unsigned (:41-42)
         }
-#ifdef FSV_OLD_SUB      // experiment: the three-instruction __vsub2 forms (zc then carries a low byte of 1 that must be masked away)
-        zc &= 0xff00ff00u;
-        U[k] = __vsub2(zc, vt1);
-        V[k] = __vsub2(zc, ut);
-        const uint32_t nz = __vsub2(0u, zc);      // -zc
-        const uint32_t n1 = __vadd2(K.kQ, nz);
-        const uint32_t kq2 = K.kQ2;
-#else
-        U[k] = __vadd2(zc, ~vt1);
-        V[k] = __vadd2(zc, ~ut);
-        const uint32_t nz = ~zc;
-        const uint32_t n1 = __vadd2(K.kQp, nz);
-        const uint32_t kq2 = K.kQ2p;
-#endif
+        U[k] = not_fma(__vadd2(nz, vt1), ALL1);
+        V[k] = not_fma(__vadd2(nz, ut), ALL1);
+        const uint32_t n1 = __vadd2(K.kQ1, nz);
+        const uint32_t kq2 = K.kQ21;
         uint32_t fl = 0;
         if (RIGHT) {
             // right alignment sets a continuation bit when the gap value is >= 0 BEFORE the max with 0 (:212-218),
@@ -237,7 +241,10 @@ __device__ __forceinline__ void dpx_cells(uint32_t (&U)[8], uint32_t (&V)[8], ui
                 if (TB) fl = __vmins2(xa, oE) + __vmins2(ya, oF);
             }
         }
-        if (TB) tbw[k] = (fl & 0x00780078u) | code;      // (left) the low 3 bits of fl hold the sum of the codes (< 8)
+        // flags | code in the low byte of each half, in ONE LOP3: (fl & m) | (zk & ~m).  The low 3 bits of fl (left: the sum of the codes,
+        // < 8) are masked away, bits 3..7 of zk's low byte are 0 (codes < 8), and the high bytes (zk's value) are never looked at below
+        // (inline PTX: the compiler splits the C expression into two LOP3s, one per immediate)
+        if (TB) asm("lop3.b32 %0, %1, %2, 0x00780078, 0xE4;" : "=r"(tbw[k]) : "r"(fl), "r"(zk));      // 0xE4 = (a & c) | (b & ~c)
     }
     if (TB) {   // 16 traceback bytes in lane order (:195)
         const uint32_t a01 = prmt(tbw[0], tbw[1], 0x6240u), a23 = prmt(tbw[2], tbw[3], 0x6240u);
@@ -317,6 +324,8 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
 #endif
     const unsigned FULL = 0xffffffffu;
     const DpxK& K = P.K;
+    uint32_t ALL1 = 0xffffffffu;
+    asm volatile("" : "+r"(ALL1));     // opaque: see not_fma
     const uint32_t extSel = DUAL ? 0xB391u : 0x4341u;                  // int8 (signed / unsigned) -> int16
     int32_t* table = C.page_tables + (int64_t)blockIdx.x * C.max_pages_per_task;
     int pending = -1;
@@ -591,7 +600,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                     const uint32_t XT0 = prmt(nbX, X[7], 0x5432u), VT0 = prmt(nbV, V[7], 0x5432u);
                     const uint32_t X2T0 = DUAL ? prmt(nbX2, X2[7], 0x5432u) : 0;
                     uint4 o;
-                    dpx_cells<DUAL, TB, RIGHT>(U, V, X, Y, X2, Y2, S, XT0, VT0, X2T0, K, o);
+                    dpx_cells<DUAL, TB, RIGHT>(U, V, X, Y, X2, Y2, S, XT0, VT0, X2T0, K, ALL1, o);
                     if (TB && (!SEG || r >= r_own)) *reinterpret_cast<uint4*>(tb_page + (int64_t)tb_rip * T.pitch + (base - st)) = o;
                     if (APPROX) approx_post(base);
                     else {
@@ -656,13 +665,14 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                     const bool lo_edge = Vt == st_, hi_edge = Vt == en_;
                     {   // lane c now faces query[r - base - c]; the lowest vector of the band reads its new base
                         // from memory, one antidiagonal ahead (qpre) so that the load is off the critical path
-                        if (lo_edge && !rearmed && qpre_r != r) { const int j = r - base; const uint32_t c0 = (j >= 0 && j < qlen) ? (uint32_t)query[j] : 0u; qpre = (c0 & 3u) | (c0 > 3u ? 4u : 0u); }
+                        // (qpre is the RAW byte: anything derived from it here would make the warp wait for the load at once)
+                        if (lo_edge && !rearmed && qpre_r != r) { const int j = r - base; qpre = (j >= 0 && j < qlen) ? (uint32_t)query[j] : 0u; }
                         const uint32_t q0 = lo_edge ? (qpre & 3u) : (nbQ >> 30);
                         qw = rearmed ? qw : ((qw << 2) | q0);
-                        if (wild && !rearmed) amb = (amb & 0xffff0000u) | (((amb << 1) | (lo_edge ? (qpre >> 2) : nbA)) & 0xffffu);
+                        if (wild && !rearmed) amb = (amb & 0xffff0000u) | (((amb << 1) | (lo_edge ? (qpre > 3u ? 1u : 0u) : nbA)) & 0xffffu);
                         int st0n, en0n;
                         band_limits(r + 1, qlen, tlen, w, st0n, en0n);
-                        if (Vt == (st0n >> 4)) { const int j = r + 1 - base; const uint32_t c0 = (j >= 0 && j < qlen) ? (uint32_t)query[j] : 0u; qpre = (c0 & 3u) | (c0 > 3u ? 4u : 0u); qpre_r = r + 1; }
+                        if (Vt == (st0n >> 4)) { const int j = r + 1 - base; qpre = (j >= 0 && j < qlen) ? (uint32_t)query[j] : 0u; qpre_r = r + 1; }
                     }
                     {   // profile stores (:126-140): whole 16-lane stores from st0, so the last one overhangs en0
                         const int store_end = st0 + ((en0 - st0) >> 4) * 16 + 15;
@@ -712,7 +722,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                         }
 
                         uint4 o;
-                        dpx_cells<DUAL, TB, RIGHT>(U, V, X, Y, X2, Y2, S, XT0, VT0, X2T0, K, o);
+                        dpx_cells<DUAL, TB, RIGHT>(U, V, X, Y, X2, Y2, S, XT0, VT0, X2T0, K, ALL1, o);
                         if (TB && (!SEG || r >= r_own)) *reinterpret_cast<uint4*>(tb_page + (int64_t)tb_rip * T.pitch + (base - st)) = o;
                         if (APPROX) approx_post(base);
                         else {
