@@ -106,6 +106,8 @@ __device__ __forceinline__ uint4 lds128(uint32_t a)
 }
 __device__ __forceinline__ void sts128(uint32_t a, uint4 v) { asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
 __device__ __forceinline__ void atom_min_shared(uint32_t a, uint32_t v) { asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void red_max_shared(uint32_t a, int32_t v) { asm volatile("red.shared.max.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(x), "r"(y) : "memory"); }
 
 // resident CTAs per SM the register budget is tuned for
 template <int NW> struct DpxOcc { static constexpr int value = NW == 1 ? 12 : NW == 2 ? 6 : NW == 4 ? 3 : 2; };
@@ -306,11 +308,12 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
     using KC = DpxConst<DUAL, RIGHT>;
     // one shared block, addressed from a single base register:
     //   edge slots [2 parities][NW] x 32 B : {x, v, x2, qw} of lane 15 of each warp's last vector, then its H and wildcard bit
-    //   per-warp max H, ring over 3 antidiagonals; tie key / H[en0] / H[st0] rings; stop flag; task index;
+    //   {tie key of antidiagonal j, CTA-wide max H of antidiagonal j+1} x 3 (rings over 3 antidiagonals: the pair is what thread 0
+    //   resets with one store per iteration; INT32_MAX as a maximum = "stop": z-drop, or a cancelled segment); H[en0] / H[st0] rings; task index;
     //   traceback pages the task holds (thread 0's; fewer than tb_pages = a lazily growing task);
     //   APPROX: v[t*] and u[t*+1] of the followed cell, by antidiagonal parity
-    constexpr uint32_t OFF_EDGE = 0, OFF_MH = 2 * NW * 32, OFF_KEY = OFF_MH + 3 * NW * 4, OFF_HEN0 = OFF_KEY + 12,
-                       OFF_HST0 = OFF_HEN0 + 12, OFF_STOP = OFF_HST0 + 12, OFF_TASK = OFF_STOP + 4, OFF_HELD = OFF_TASK + 4, OFF_APV = OFF_HELD + 4, OFF_APU = OFF_APV + 8, OFF_SEG = OFF_APU + 8, OFF_SCAN = OFF_SEG + 8,
+    constexpr uint32_t OFF_EDGE = 0, OFF_KM = 2 * NW * 32, OFF_HEN0 = OFF_KM + 24,
+                       OFF_HST0 = OFF_HEN0 + 12, OFF_TASK = OFF_HST0 + 12, OFF_HELD = OFF_TASK + 4, OFF_APV = OFF_HELD + 4, OFF_APU = OFF_APV + 8, OFF_SEG = OFF_APU + 8, OFF_SCAN = OFF_SEG + 8,
                        SH_BYTES = OFF_SCAN + (SEG ? 4 * NW + 4 * NT : 0);      // SEG: scratch of the H re-anchoring scan
     __shared__ __align__(16) uint32_t sh_raw[(SH_BYTES + 15) / 16 * 4];
     uint32_t sb = (uint32_t)__cvta_generic_to_shared(sh_raw);
@@ -337,7 +340,8 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
             int held = 0;
             if (SEG) sts32(sb + OFF_TASK, (uint32_t)(seg_redo >= 0 ? seg_redo : queue_take(P.Q, 0)));
             else sts32(sb + OFF_TASK, (uint32_t)next_task(C, P.Q, table, pending, true, held));
-            sts32(sb + OFF_STOP, (uint32_t)INT32_MAX); sts32(sb + OFF_HELD, (uint32_t)held);
+            sts32(sb + OFF_KM + 8u * 2u + 4u, (uint32_t)INT32_MIN);      // the maximum slot of the first antidiagonal (the others are reset on the way)
+            sts32(sb + OFF_HELD, (uint32_t)held);
         }
         __syncthreads();
         const int wi = (int)lds32(sb + OFF_TASK);      // task index, or (SEG) segment index
@@ -430,9 +434,15 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
             const int par = r & 1, ppar = par ^ 1;
             // a later segment of a task that z-dropped inside segment 0: stop through the same flag a z-drop uses (posted at
             // iteration r, seen by every thread in section (A) of iteration r+1)
-            if (SEG && segmode && G.index > 0 && (r & 255) == 0 && r > rz + 1 && tid == 0 && __ldcg(C.seg_cancel + T.seg_id) != 0)
-                sts32(sb + OFF_STOP, (uint32_t)r);
             const int s3m1 = s3 == 0 ? 2 : s3 - 1, s3m2 = s3 == 2 ? 0 : s3 + 1;   // (r-1)%3, (r-2)%3
+            // key of antidiagonal j: OFF_KM + 8j; maximum of antidiagonal j: OFF_KM + 8((j+2)%3) + 4
+            const uint32_t a_key = sb + OFF_KM + 8u * (uint32_t)s3, a_key1 = sb + OFF_KM + 8u * (uint32_t)s3m1, a_key2 = sb + OFF_KM + 8u * (uint32_t)s3m2;
+            const uint32_t a_max = a_key1 + 4u, a_max1 = a_key2 + 4u;
+            if (SEG && segmode && G.index > 0 && (r & 255) == 0 && r > rz + 1 && tid == 0 && __ldcg(C.seg_cancel + T.seg_id) != 0)
+                red_max_shared(a_max, INT32_MAX);
+            // maximum of antidiagonal r-1 (every warp's red.max behind the last barrier), fetched early
+            int32_t m_prev = INT32_MIN;
+            if (!APPROX && r >= rz + 1) m_prev = (int32_t)lds32(a_max1);
 
             // ---- neighbour's lane 15 as it stood after the previous antidiagonal
             uint32_t nbX = __shfl_up_sync(FULL, X[7], 1), nbV = __shfl_up_sync(FULL, V[7], 1);
@@ -479,7 +489,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
             }
             // ---- (A) antidiagonal d = r-2 is final: bookkeeping (ksw2_extz2_sse.c:262-269)
             if (!APPROX && r >= rz + 2) {
-                if ((int)lds32(sb + OFF_STOP) < r) { dropped = true; break; }      // set during an EARLIER iteration: every thread agrees
+                if (m_prev == INT32_MAX) { dropped = true; break; }      // "stop" posted during the previous iteration: every thread agrees
                 maxrun = max(maxrun, M2);
                 const int d = r - 2;
                 if (SEG && segmode) {
@@ -489,7 +499,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                         int st0d, en0d;
                         band_limits(d, qlen, tlen, w, st0d, en0d);
                         int max_t = en0d;
-                        const uint32_t bk = lds32(sb + OFF_KEY + 4u * s3m2);
+                        const uint32_t bk = lds32(a_key2);
                         if (bk != 0) max_t = (int)((bk - 1u) & ((1u << 26) - 1u));
                         if (lane == 0) {
                             const int32_t hen0 = en0d == tlen - 1 ? (int32_t)lds32(sb + OFF_HEN0 + 4u * s3m2) : FSV_NEG_INF;
@@ -501,7 +511,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                         // would only be wasted work, and they are what a short batch would wait for: tell them to stop
                         if (G.index == 0 && ez.apply_zdrop(M2, d, max_t, T.zdrop, sc.e_drop)) {
                             dropped = true;
-                            if (lane == 0) { sts32(sb + OFF_STOP, (uint32_t)r); atomicExch(C.seg_cancel + T.seg_id, 1); }
+                            if (lane == 0) { red_max_shared(a_max, INT32_MAX); atomicExch(C.seg_cancel + T.seg_id, 1); }
                         }
                     }
                 } else
@@ -511,7 +521,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                     cells += en0d - st0d + 1;
                     int max_t = en0d;
                     if (nt2) {
-                        const uint32_t bk = lds32(sb + OFF_KEY + 4u * s3m2);
+                        const uint32_t bk = lds32(a_key2);
                         if (bk != 0) max_t = (int)((bk - 1u) & ((1u << 26) - 1u));
                     }
                     int32_t h_last = FSV_NEG_INF;
@@ -523,18 +533,18 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                         const int32_t h = (int32_t)lds32(sb + OFF_HST0 + 4u * s3m2);
                         if (h > ez.mqe) { ez.mqe = h; ez.mqe_t = st0d; }
                     }
-                    if (ez.apply_zdrop(M2, d, max_t, T.zdrop, sc.e_drop)) { dropped = true; if (lane == 0) sts32(sb + OFF_STOP, (uint32_t)r); }
+                    if (ez.apply_zdrop(M2, d, max_t, T.zdrop, sc.e_drop)) { dropped = true; if (lane == 0) red_max_shared(a_max, INT32_MAX); }
                     else if (d == n_diag - 1 && en0d == tlen - 1) ez.score = h_last;            // H[tlen-1]
                 }
                 if (d == stop_r - 1) {     // every computed antidiagonal is final
                     if (NW > 1) __syncthreads(); else __syncwarp();
-                    if ((int)lds32(sb + OFF_STOP) <= r) dropped = true;
+                    if ((int32_t)lds32(a_max) == INT32_MAX) dropped = true;      // posted during THIS iteration (an earlier one left the loop above)
                     break;
                 }
             }
             // ---- (B) antidiagonal r-1: its maximum, and (only if observable, ksw2.h:164-174) who holds it
             if (!APPROX && r >= rz + 1 && r - 1 < stop_r) {
-                const int32_t m = __reduce_max_sync(FULL, lane < NW ? (int32_t)lds32(sb + OFF_MH + 4u * (uint32_t)(s3m1 * NW + lane)) : INT32_MIN);
+                const int32_t m = m_prev;
                 M1 = m;
                 const int32_t mr = max(maxrun, M2);      // ez.max once r-2 is accounted for
                 nt1 = m > mr || (T.zdrop >= 0 && mr - m > T.zdrop) || (SEG && segmode);      // a segment cannot know: always
@@ -562,10 +572,10 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                         }
                         if (!body && tail) key = 1u + (4u << 26) + (uint32_t)(base + __ffs(tail) - 1);
                     }
-                    atom_min_shared(sb + OFF_KEY + 4u * s3m1, key);
+                    atom_min_shared(a_key1, key);
                 }
             }
-            if (!APPROX && tid == 0) sts32(sb + OFF_KEY + 4u * s3, 0xffffffffu);
+            if (!APPROX && tid == 0) sts64(a_key, 0xffffffffu, (uint32_t)INT32_MIN);      // key of r (posted at r+1), maximum of r+1
 
             // ---- (C) compute antidiagonal r
             int st0 = 0, en0 = -1;
@@ -588,7 +598,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
             }
             act_p = false;
             if (valid) {
-                const int st = round_st(st0), en = round_en(en0), st_ = st >> 4, en_ = en >> 4;
+                const int st = st0 & ~15, en = en0 | 15, st_ = st0 >> 4, en_ = en0 >> 4;      // round_st / round_en of 0 <= st0 <= en0 (:116)
                 int32_t habs = INT32_MIN;      // this thread's best H over its in-band lanes
                 // a warp whose 32 vectors all lie strictly inside the band takes the short path
                 const bool inner = Vt > st_ && Vt < en_;
@@ -613,7 +623,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                     const uint32_t pm = __vimax3_s16x2(__vimax3_s16x2(Hr[0], Hr[1], Hr[2]), __vimax3_s16x2(Hr[3], Hr[4], Hr[5]), __vmaxs2(Hr[6], Hr[7]));
                     const int mrel = max(sext16(pm), sext16(pm >> 16));
                     habs = Hb + mrel;
-                    if ((r & 31) == 31) {   // keep the relative scores small
+                    if (__builtin_expect((r & 31) == 31, 0)) {   // keep the relative scores small
                         Hb += mrel;
                         const uint32_t dd = both((uint32_t)mrel & 0xffffu);
 #pragma unroll
@@ -629,7 +639,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                     else if (NW == 1) { int32_t h = __shfl_sync(FULL, Hb + sext16(Hr[7] >> 16), 31); if (lane == 0) nbH = h; }
                     else if (lane == 0 && r > rz) nbH = (int32_t)lds32(sb + OFF_EDGE + (uint32_t)(ppar * NW + (warp + NW - 1) % NW) * 32u + 16u);
                     bool rearmed = false;
-                    if (Vt < st_) {            // a vector that fell below the band re-arms NT vectors to the right
+                    if (__builtin_expect(Vt < st_, 0)) {            // a vector that fell below the band re-arms NT vectors to the right
                         Vt += NT;
                         while (Vt < st_) Vt += NT;
                         rearmed = true;
@@ -690,10 +700,12 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                         const int ce = en0 - base; // lane of en0 inside this vector (meaningful when hi_edge)
                         {   // carries of the lowest vector (:118-122)
                             // [last_st, last_en] = rounded range of the previous antidiagonal (:287), rebuilt from its exact limits
-                            const bool inl = st > 0 && st - 1 >= round_st(st0p) && st - 1 <= round_en(en0p);
-                            uint32_t vfirst;       // first column: v1 of an antidiagonal that starts at t = 0
-                            if (DUAL) vfirst = hi8(r == 0 ? -K.qe : r < sc.long_thres ? -sc.e : r == sc.long_thres ? sc.long_diff : -sc.e2);
-                            else vfirst = hi8(r ? sc.q : 0);
+                            const bool inl = st > 0 && st - 1 >= (st0p & ~15) && st - 1 <= (en0p | 15);
+                            uint32_t vfirst = 0;   // first column: v1 of an antidiagonal that starts at t = 0 (only while r <= w)
+                            if (__builtin_expect(st == 0, 0)) {
+                                if (DUAL) vfirst = hi8(r == 0 ? -K.qe : r < sc.long_thres ? -sc.e : r == sc.long_thres ? sc.long_diff : -sc.e2);
+                                else vfirst = hi8(r ? sc.q : 0);
+                            }
                             const uint32_t x1 = inl ? (XT0 & 0xffffu) : (K.gX & 0xffffu);
                             const uint32_t v1 = inl ? (VT0 & 0xffffu) : st > 0 ? (K.gU & 0xffffu) : vfirst;
                             const uint32_t x21 = inl ? (X2T0 & 0xffffu) : (K.gX2 & 0xffffu);
@@ -705,7 +717,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                                 if (v1 & 0x8000u) { V[0] = (V[0] & 0xffff0000u) | 0xff00u; V[1] = (V[1] & 0xffff0000u) | 0xff00u; V[2] = (V[2] & 0xffff0000u) | 0xff00u; }
                             }
                         }
-                        if (en >= r) {             // first row (:123): only while r <= w
+                        if (__builtin_expect(en >= r, 0)) {             // first row (:123): only while r <= w
                             if ((r >> 4) == Vt) {
                                 uint32_t eu;
                                 if (DUAL) eu = hi8(r == 0 ? -K.qe : r < sc.long_thres ? -sc.e : r == sc.long_thres ? sc.long_diff : -sc.e2);
@@ -756,7 +768,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                         if (lo_edge && r - st0 == qlen - 1) sts32(sb + OFF_HST0 + 4u * s3, (uint32_t)(Hb + sext16(get_cell(Hr, st0 - base))));
                         const int mrel = max(sext16(pm), sext16(pm >> 16));
                         habs = Hb + mrel;
-                        if ((r & 31) == 31) {   // keep the relative scores small
+                        if (__builtin_expect((r & 31) == 31, 0)) {   // keep the relative scores small
                             Hb += mrel;
                             const uint32_t dd = both((uint32_t)mrel & 0xffffu);
 #pragma unroll
@@ -820,9 +832,9 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
                 }
                 if (!APPROX) {
                     const int32_t wmax = __reduce_max_sync(FULL, habs);
-                    if (lane == 0) sts32(sb + OFF_MH + 4u * (uint32_t)(s3 * NW + warp), (uint32_t)wmax);
+                    if (lane == 0) red_max_shared(a_max, wmax);
                 }
-                if (TB && (!SEG || r >= r_own) && ++tb_rip == T.rows_per_page) {
+                if (TB && (!SEG || r >= r_own) && __builtin_expect(++tb_rip == T.rows_per_page, 0)) {
                     tb_rip = 0; ++tb_pg;
                     if (tb_pg < T.tb_pages) tb_page = C.pool.base + (int64_t)(SEG ? __ldcg(table + tb_pg) : table[tb_pg]) * C.pool.page_bytes;
                     // (thread 0 of a lazily growing task) one page ahead: the CTA reads table[tb_pg + 1] a whole page of antidiagonals from now
