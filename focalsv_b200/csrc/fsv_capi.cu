@@ -21,6 +21,7 @@
 #include "fsv_backtrack.cuh"
 #include "fsv_common.cuh"
 #include "fsv_fill_dpx.cuh"
+#include "fsv_fill_ew.cuh"
 #include "fsv_fill_exact.cuh"
 #include "fsv_peaks.cuh"
 #include "fsv_editdist.cuh"
@@ -59,6 +60,7 @@ struct fsv_ctx {
                                      // those whose chain of antidiagonals would outlast 60 % of the batch's throughput time)
     int segment_warm_pct = 400;      // cold-start lead of a segment, in percent of the band width (+1024 antidiagonals)
     int segment_align_pages = 0;     // 0 = segments are multiples of 1024 antidiagonals (default), 1 = whole traceback pages
+    int ew_kernel = 1;               // mainstream tasks run on the edge-warp kernel (fsv_fill_ew.cuh); 0 = everything on fsv_fill_dpx_kernel
     int segment_auto_pct = 70;       // auto mode: tasks whose chain of antidiagonals outlasts this share of the batch's estimated time are segmented
     int segment_extz = 1;            // auto mode: 1 = extension (EXTZ_ONLY) tasks are segmented too, 0 = global tasks only
     int64_t segment_rows = 0;        // target antidiagonals per segment, rounded up to 1024 (0 = auto: 4 x or 2 x the warm-up)
@@ -260,6 +262,7 @@ extern "C" int fsv_set_option(fsv_ctx* c, const char* key, int64_t value)
     if (!strcmp(key, "segment_slots") || !strcmp(key, "segment_pool_pct") || !strcmp(key, "segment_pool_pct_bound")) return FSV_OK;   // ABI 3 tunables of the static page slots: accepted, no effect
     if (!strcmp(key, "segment_auto_pct")) { if (value < 1 || value > 1000) return FSV_ERR_INVALID; c->segment_auto_pct = (int)value; return FSV_OK; }
     if (!strcmp(key, "segment_align_pages")) { c->segment_align_pages = value != 0; return FSV_OK; }
+    if (!strcmp(key, "ew_kernel")) { c->ew_kernel = value != 0; return FSV_OK; }
     if (!strcmp(key, "segment_extz")) { c->segment_extz = value != 0; return FSV_OK; }
     if (!strcmp(key, "segment_rows")) { if (value != 0 && value < 1024) return FSV_ERR_INVALID; c->segment_rows = value; return FSV_OK; }
     if (!strcmp(key, "pool_stall_ms")) { if (value < 100) return FSV_ERR_INVALID; c->pool_stall_ms = (int)value; return FSV_OK; }
@@ -480,6 +483,8 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
                 b->is_dpx[i] = 1;
                 d.nw = dpx_class_of(dpx_warps_needed(d));
                 d.tb_mode = (t.flag & FSV_EZ_RIGHT) ? 0 : b->dual ? 4 : 2;      // right alignment stores ksw2's d itself
+                // (kind 1: pad_ = main warps on the edge-warp kernel, 0 = that kernel does not take the task)
+                if (c->ew_kernel && ew_supports(b->sc, d, wild[i] != 0)) d.pad_ = dpx_class_of(ew_warps_needed(d));
             }
         }
     }
@@ -674,20 +679,25 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
             const DevTask& d = b->tasks[ti];
             if (is_seg[(size_t)ti]) continue;
             if (kind == 0) { if (b->is_dpx[ti]) continue; }
-            else if (!b->is_dpx[ti] || d.nw != nw || ((d.flag & FSV_EZ_SCORE_ONLY) ? ((d.flag & FSV_EZ_APPROX_MAX) ? 3 : 0) : (d.flag & FSV_EZ_RIGHT) ? 2 : 1) != with_tb || (int)is_excl[ti] != excl) continue;
+            else {
+                // with_tb: 0 score only, 1 traceback (ties left), 2 traceback (ties right), 3 score only + approximate maximum, 4 = 1 on the edge-warp kernel
+                const int mode = (d.flag & FSV_EZ_SCORE_ONLY) ? ((d.flag & FSV_EZ_APPROX_MAX) ? 3 : 0) : (d.flag & FSV_EZ_RIGHT) ? 2 : d.pad_ > 0 ? 4 : 1;
+                if (!b->is_dpx[ti] || (mode == 4 ? d.pad_ : d.nw) != nw || mode != with_tb || (int)is_excl[ti] != excl) continue;
+            }
             b->work.push_back(ti);
             if (kind == 0 && d.kind == 1 && d.pitch + 96 > c->exact_smem_lanes) ws_need = std::max<int64_t>(ws_need, d.pitch + 96);
         }
         L.count = (int)b->work.size() - L.begin;
         if (!L.count) return;
-        L.grid = kind == 0 ? exact_grid(c, b->dual, L.count) : excl ? std::min(L.count, c->sm_count) : dpx_grid(c->sm_count, b->dual, with_tb, nw, L.count);
+        L.grid = kind == 0 ? exact_grid(c, b->dual, L.count) : excl ? std::min(L.count, c->sm_count)
+                 : with_tb == 4 ? (b->dual ? ew_grid_1(c->sm_count, nw, L.count) : ew_grid_0(c->sm_count, nw, L.count)) : dpx_grid(c->sm_count, b->dual, with_tb, nw, L.count);
         L.table_off = table_off;
         table_off += (int64_t)L.grid * b->max_pages_per_task;
         b->launches.push_back(L);
     };
     static const int kClasses[5] = {8, 6, 4, 2, 1};
-    for (int cls : kClasses) for (int with_tb = 3; with_tb >= 0; --with_tb) add_launch(1, cls, with_tb, 1);
-    for (int cls : kClasses) for (int with_tb = 3; with_tb >= 0; --with_tb) add_launch(1, cls, with_tb, 0);
+    for (int cls : kClasses) for (int with_tb = 4; with_tb >= 0; --with_tb) add_launch(1, cls, with_tb, 1);
+    for (int cls : kClasses) for (int with_tb = 4; with_tb >= 0; --with_tb) add_launch(1, cls, with_tb, 0);
     add_launch(0, 0, 0, 0);
     tr.lap("create: sort + work lists");
     b->ws_lanes = ws_need ? pow2_at_least(ws_need) : 0;
@@ -872,7 +882,8 @@ extern "C" int fsv_batch_run(fsv_batch* b)
         R.slot_base = slot_base; slot_base += L.grid;
         if (L.kind == 1) {
             DpxParams D{R, Q, DpxK{}, 0};
-            rc = dpx_launch(ks, b->dual, L.with_tb, L.nw, L.grid, L.excl != 0, D, &c->last_error);
+            rc = L.with_tb == 4 ? (b->dual ? ew_launch_1(ks, L.nw, L.grid, L.excl != 0, D, &c->last_error) : ew_launch_0(ks, L.nw, L.grid, L.excl != 0, D, &c->last_error))
+                                : dpx_launch(ks, b->dual, L.with_tb, L.nw, L.grid, L.excl != 0, D, &c->last_error);
             if (rc != FSV_OK) return rc;
         } else {
             FillParams P{R, Q, c->d_ws, b->ws_lanes, c->exact_smem_lanes};

@@ -5,6 +5,7 @@
 #include <string>
 
 #include "fsv_fill_dpx.cuh"
+#include "fsv_fill_ew.cuh"
 
 #ifndef FSV_VARIANT_DUAL
 #error "compile with -DFSV_VARIANT_DUAL=0|1 -DFSV_VARIANT_TBM=0|1|2|3"
@@ -28,6 +29,12 @@ int FSV_CAT3(dpx_launch_, FSV_VARIANT_DUAL, FSV_VARIANT_TBM)(cudaStream_t stream
 int FSV_CAT3(dpx_launch_seg_, FSV_VARIANT_DUAL, )(cudaStream_t stream, int sm_count, int nw, int n_segs, const DpxParams& P, std::string* err)
 {
     return dpx_launch_seg_nw<FSV_VARIANT_DUAL != 0>(stream, sm_count, nw, n_segs, P, err);
+}
+// the edge-warp kernel (fsv_fill_ew.cuh): left-aligned traceback only
+int FSV_CAT3(ew_grid_, FSV_VARIANT_DUAL, )(int sm_count, int nw, int n_tasks) { return ew_grid_nw<FSV_VARIANT_DUAL != 0>(sm_count, nw, n_tasks); }
+int FSV_CAT3(ew_launch_, FSV_VARIANT_DUAL, )(cudaStream_t stream, int nw, int grid, bool excl, const DpxParams& P, std::string* err)
+{
+    return ew_launch_nw<FSV_VARIANT_DUAL != 0>(stream, nw, grid, excl, P, err);
 }
 #endif
 
