@@ -19,7 +19,7 @@ EZ_APPROX_DROP = 0x10
 EZ_EXTZ_ONLY = 0x40
 EZ_REV_CIGAR = 0x80
 
-PLAN_DPX, PLAN_GENERAL, PLAN_SEGMENTED, PLAN_EXCLUSIVE = 1, 2, 4, 8
+PLAN_DPX, PLAN_GENERAL, PLAN_SEGMENTED, PLAN_EXCLUSIVE, PLAN_EDGE_WARP = 1, 2, 4, 8, 16
 
 OK = 0
 ERR_NO_DEVICE = -1

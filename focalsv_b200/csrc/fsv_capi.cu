@@ -60,7 +60,8 @@ struct fsv_ctx {
                                      // those whose chain of antidiagonals would outlast 60 % of the batch's throughput time)
     int segment_warm_pct = 400;      // cold-start lead of a segment, in percent of the band width (+1024 antidiagonals)
     int segment_align_pages = 0;     // 0 = segments are multiples of 1024 antidiagonals (default), 1 = whole traceback pages
-    int ew_kernel = 1;               // mainstream tasks run on the edge-warp kernel (fsv_fill_ew.cuh); 0 = everything on fsv_fill_dpx_kernel
+    int ew_kernel = 1;               // mainstream tasks run on the edge-warp kernel (fsv_fill_ew.cuh): 1 = those that need up to 4 main warps (bands up to
+                                     // about 2 000; seven warps of 128 registers spill, so wider bands stay with fsv_fill_dpx_kernel), 2 = all of them, 0 = none
     int segment_auto_pct = 70;       // auto mode: tasks whose chain of antidiagonals outlasts this share of the batch's estimated time are segmented
     int segment_extz = 1;            // auto mode: 1 = extension (EXTZ_ONLY) tasks are segmented too, 0 = global tasks only
     int64_t segment_rows = 0;        // target antidiagonals per segment, rounded up to 1024 (0 = auto: 4 x or 2 x the warm-up)
@@ -262,7 +263,7 @@ extern "C" int fsv_set_option(fsv_ctx* c, const char* key, int64_t value)
     if (!strcmp(key, "segment_slots") || !strcmp(key, "segment_pool_pct") || !strcmp(key, "segment_pool_pct_bound")) return FSV_OK;   // ABI 3 tunables of the static page slots: accepted, no effect
     if (!strcmp(key, "segment_auto_pct")) { if (value < 1 || value > 1000) return FSV_ERR_INVALID; c->segment_auto_pct = (int)value; return FSV_OK; }
     if (!strcmp(key, "segment_align_pages")) { c->segment_align_pages = value != 0; return FSV_OK; }
-    if (!strcmp(key, "ew_kernel")) { c->ew_kernel = value != 0; return FSV_OK; }
+    if (!strcmp(key, "ew_kernel")) { if (value < 0 || value > 2) return FSV_ERR_INVALID; c->ew_kernel = (int)value; return FSV_OK; }
     if (!strcmp(key, "segment_extz")) { c->segment_extz = value != 0; return FSV_OK; }
     if (!strcmp(key, "segment_rows")) { if (value != 0 && value < 1024) return FSV_ERR_INVALID; c->segment_rows = value; return FSV_OK; }
     if (!strcmp(key, "pool_stall_ms")) { if (value < 100) return FSV_ERR_INVALID; c->pool_stall_ms = (int)value; return FSV_OK; }
@@ -484,7 +485,10 @@ extern "C" int fsv_batch_create(fsv_ctx* c, const fsv_scoring* scoring,
                 d.nw = dpx_class_of(dpx_warps_needed(d));
                 d.tb_mode = (t.flag & FSV_EZ_RIGHT) ? 0 : b->dual ? 4 : 2;      // right alignment stores ksw2's d itself
                 // (kind 1: pad_ = main warps on the edge-warp kernel, 0 = that kernel does not take the task)
-                if (c->ew_kernel && ew_supports(b->sc, d, wild[i] != 0)) d.pad_ = dpx_class_of(ew_warps_needed(d));
+                if (c->ew_kernel && ew_supports(b->sc, d, wild[i] != 0)) {
+                    const int nwm = dpx_class_of(ew_warps_needed(d));
+                    if (nwm <= 4 || c->ew_kernel >= 2) d.pad_ = nwm;
+                }
             }
         }
     }
@@ -1088,6 +1092,7 @@ extern "C" int fsv_batch_plan(const fsv_batch* b, int32_t* plan)
     for (size_t i = 0; i < b->n; ++i) {
         int32_t v = 0;
         if (b->tasks[i].kind == 1) v |= b->is_dpx[i] ? FSV_PLAN_DPX : FSV_PLAN_GENERAL;
+        if (b->tasks[i].kind == 1 && b->is_dpx[i] && b->tasks[i].pad_ > 0 && !(i < b->is_seg.size() && b->is_seg[i])) v |= FSV_PLAN_EDGE_WARP;
         if (i < b->is_seg.size() && b->is_seg[i]) v |= FSV_PLAN_SEGMENTED | ((int32_t)b->seg_tasks[(size_t)b->tasks[i].seg_id].n_segs << 16);
         if (i < b->is_excl.size() && b->is_excl[i]) v |= FSV_PLAN_EXCLUSIVE;
         v |= (b->tasks[i].nw & 0xf) << 8;

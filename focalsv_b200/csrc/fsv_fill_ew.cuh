@@ -20,6 +20,9 @@
 // bases, not segmented, band >= 32, both sequences >= 64 bases; everything else stays with fsv_fill_dpx_kernel, which is also
 // what this kernel is tested against (same oracle digests).
 #pragma once
+#include <cstdio>
+#include <cstdlib>
+
 #include "fsv_fill_dpx.cuh"
 
 namespace fsv {
@@ -573,6 +576,7 @@ inline int ew_grid_one(int sm_count, int n_tasks)
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fsv_fill_ew_kernel<DUAL, NWM, false>, (NWM + 1) * 32, 0) != cudaSuccess) { cudaGetLastError(); per_sm = 1; }
     if (per_sm < 1) per_sm = 1;
+    if (getenv("FSV_TRACE")) fprintf(stderr, "[fsv] edge-warp kernel, %d main warps: %d CTAs per SM\n", NWM, per_sm);
     return std::max(1, std::min(n_tasks, sm_count * per_sm));
 }
 template <bool DUAL, int NWM>

@@ -148,6 +148,8 @@ int fsv_get_stats(const fsv_ctx* ctx, fsv_stats* out);
  *   "segment_align_pages"     1 = segments are whole traceback pages (default), 0 = any multiple of 1024 antidiagonals (experiment)
  *   "segment_pool_pct_bound"  the pool share when the batch's traceback does not fit the pool and it is throughput-bound (default 25)
  *   "segment_extz"            auto mode: 1 = extension (EXTZ_ONLY) tasks are segmented too (default), 0 = global tasks only
+ *   "ew_kernel"               which tasks run on the edge-warp fill kernel (left-aligned traceback, no wildcard bases, band >= 32): 1 = those whose band needs
+ *                             up to 4 main warps (default), 2 = all of them, 0 = none (everything on the one-vector-per-thread kernel)
  *   "force_exact"             1 = int8-exact general kernel only
  *   "exact_smem_lanes", "force_excl"   kernel experiments */
 int fsv_set_option(fsv_ctx* ctx, const char* key, int64_t value);
@@ -183,6 +185,7 @@ int fsv_batch_timeline(fsv_batch* batch, int64_t* start_end_ns);
 #define FSV_PLAN_GENERAL   0x2   /* runs on the general int8-exact kernel */
 #define FSV_PLAN_SEGMENTED 0x4   /* cut into segments that run on separate CTAs */
 #define FSV_PLAN_EXCLUSIVE 0x8   /* runs on the exclusive (one CTA per SM) launch */
+#define FSV_PLAN_EDGE_WARP 0x10  /* (with FSV_PLAN_DPX) runs on the edge-warp variant of the DPX fill kernel */
 int fsv_batch_plan(const fsv_batch* batch, int32_t* plan);
 
 /* ---- Level 1: the pipeline hook -------------------------------
