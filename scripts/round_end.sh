@@ -24,4 +24,6 @@ timeout 900 ncu --replay-mode application --metrics dram__bytes_read.sum,dram__b
 python scripts/ncu_traffic.py $out/ncu_traffic_${tag}.csv $out/bench_${tag}_n1.jsonl $out/ncu_traffic_${tag}.json
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:fsv_fill_dpx -s 1 -c 1 -f -o $out/prof_dpx_${tag} \
   python scripts/kbench.py asm5 20000 3001 592 > $out/${tag}_ncu.log 2>&1; echo "ncu full rc $?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:fsv_fill_ew -s 1 -c 1 -f -o $out/prof_ew_${tag} \
+  python scripts/kbench.py hifiasm 20000 500 1184 > $out/${tag}_ncu_ew.log 2>&1; echo "ncu full (edge-warp kernel) rc $?"
 cut -c1-300 $out/bench_${tag}_n1.jsonl; cat $out/configs_full_${tag}.log | cut -c1-260; grep GCUPS $out/kbench_${tag}.log | awk 'NR%3==0'
