@@ -376,13 +376,32 @@ struct StallWatch {
     }
 };
 
+// A CTA may KEEP the pages of the task it has just finished (table[0 .. kept)) for its next one: a batch of 10^5 small tasks (the
+// fills of the chained path, reads against a window) otherwise takes and returns one page per task under the one pool lock, which
+// then is what the batch waits for (2 x 10^5 lock hand-overs of a microsecond each).  Only short, up-front tasks; only while the pool
+// is comfortably free and no segmented task is waiting for its reserve (pool_may_keep).
+constexpr int POOL_KEEP_MAX = 8;
+__device__ __forceinline__ bool pool_may_keep(const TbPool& P, int n)
+{
+    return n > 0 && n <= POOL_KEEP_MAX && *(volatile int32_t*)P.reserve == 0 && *(volatile int32_t*)P.n_free >= (P.n_pages >> 2);
+}
+
 // Pages for task t (thread 0 only): up front, or lazily (`lazy_ok`, DPX kernels) when it is long.
-// `held` receives the pages taken now; held < tb_pages marks a lazy task.
-__device__ inline bool task_pages(const RunCtx& C, int t, int32_t* table, bool lazy_ok, int& held)
+// `held` receives the pages taken now; held < tb_pages marks a lazy task.  `kept`: pages of the CTA's previous task still in table[].
+__device__ inline bool task_pages(const RunCtx& C, int t, int32_t* table, bool lazy_ok, int& held, int& kept)
 {
     const DevTask& T = C.tasks[t];
-    if (lazy_ok && C.pool.lazy && C.pool.lazy_min_pages > 0 && T.tb_pages >= C.pool.lazy_min_pages)
-        return pool_lazy_admit(C.pool, C.slot_base + (int)blockIdx.x, T.tb_pages, T.rows_per_page, table, held);
+    const bool lazy = lazy_ok && C.pool.lazy && C.pool.lazy_min_pages > 0 && T.tb_pages >= C.pool.lazy_min_pages;
+    if (kept > 0) {
+        if (!lazy && T.tb_pages >= kept && (T.tb_pages == kept || pool_try_alloc(C.pool, T.tb_pages - kept, table + kept))) {
+            atomicAdd(C.pool.progress, 1);           // the watchdog's heartbeat
+            held = T.tb_pages; kept = 0;
+            return true;
+        }
+        pool_free(C.pool, kept, table);              // of no use for this task (or the rest is not to be had right now)
+        kept = 0;
+    }
+    if (lazy) return pool_lazy_admit(C.pool, C.slot_base + (int)blockIdx.x, T.tb_pages, T.rows_per_page, table, held);
     if (!pool_try_alloc(C.pool, T.tb_pages, table)) return false;
     held = T.tb_pages;
     return true;
@@ -390,10 +409,10 @@ __device__ inline bool task_pages(const RunCtx& C, int t, int32_t* table, bool l
 
 // One attempt of a WAITING CTA: only one waiter at a time runs the (locked, not free) admission checks, the
 // others sleep, so that the tasks that are running never queue behind a crowd of pollers for the pool lock.
-__device__ inline bool task_pages_gated(const RunCtx& C, int t, int32_t* table, bool lazy_ok, int& held)
+__device__ inline bool task_pages_gated(const RunCtx& C, int t, int32_t* table, bool lazy_ok, int& held, int& kept)
 {
     if (atomicCAS(C.pool.gate, 0, 1) != 0) return false;
-    const bool ok = task_pages(C, t, table, lazy_ok, held);
+    const bool ok = task_pages(C, t, table, lazy_ok, held, kept);
     __threadfence();
     atomicExch(C.pool.gate, 0);
     return ok;
@@ -401,19 +420,19 @@ __device__ inline bool task_pages_gated(const RunCtx& C, int t, int32_t* table, 
 
 // Picks the next task for this CTA (thread 0 only) and gets its traceback pages.
 // `pending` carries a claimed task that is still waiting for memory.  Returns the task index or -1.
-__device__ inline int next_task(const RunCtx& C, const TaskQueue& Q, int32_t* table, int& pending, bool lazy_ok, int& held)
+__device__ inline int next_task(const RunCtx& C, const TaskQueue& Q, int32_t* table, int& pending, bool lazy_ok, int& held, int& kept)
 {
     StallWatch watch;
     for (;;) {
         if (pending >= 0) {
-            if (task_pages_gated(C, pending, table, lazy_ok, held)) { int t = pending; pending = -1; return t; }
+            if (task_pages_gated(C, pending, table, lazy_ok, held, kept)) { int t = pending; pending = -1; return t; }
             int t = queue_take(Q, 1);                       // memory is short: do a small task meanwhile
             if (t >= 0) {
-                if (task_pages(C, t, table, lazy_ok, held)) return t;
+                if (task_pages(C, t, table, lazy_ok, held, kept)) return t;
                 // not even the small one fits right now: wait for running tasks to finish
                 for (;;) {
                     __nanosleep(20000);
-                    if (task_pages_gated(C, t, table, lazy_ok, held)) return t;
+                    if (task_pages_gated(C, t, table, lazy_ok, held, kept)) return t;
                     watch.poll(C.pool);
                 }
             }
@@ -422,8 +441,11 @@ __device__ inline int next_task(const RunCtx& C, const TaskQueue& Q, int32_t* ta
             continue;
         }
         int t = queue_take(Q, 0);
-        if (t < 0) return -1;
-        if (task_pages(C, t, table, lazy_ok, held)) return t;
+        if (t < 0) {
+            if (kept > 0) { pool_free(C.pool, kept, table); kept = 0; }      // the queue is empty: nothing to keep pages for
+            return -1;
+        }
+        if (task_pages(C, t, table, lazy_ok, held, kept)) return t;
         pending = t;
     }
 }

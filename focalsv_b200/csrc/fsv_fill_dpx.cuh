@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
     asm volatile("" : "+r"(ALL1));     // opaque: see not_fma
     const uint32_t extSel = DUAL ? 0xB391u : 0x4341u;                  // int8 (signed / unsigned) -> int16
     int32_t* table = C.page_tables + (int64_t)blockIdx.x * C.max_pages_per_task;
-    int pending = -1;
+    int pending = -1, kept = 0;      // (thread 0) a task claimed but still waiting for memory; pages kept from the previous task
     int seg_redo = -1;          // SEG: a segment whose cold start did not reach its predecessor's state: this CTA runs it again FROM that state
 
     for (;;) {
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
         if (tid == 0) {
             int held = 0;
             if (SEG) sts32(sb + OFF_TASK, (uint32_t)(seg_redo >= 0 ? seg_redo : queue_take(P.Q, 0)));
-            else sts32(sb + OFF_TASK, (uint32_t)next_task(C, P.Q, table, pending, true, held));
+            else sts32(sb + OFF_TASK, (uint32_t)next_task(C, P.Q, table, pending, true, held, kept));
             sts32(sb + OFF_KM + 8u * 2u + 4u, (uint32_t)INT32_MIN);      // the maximum slot of the first antidiagonal (the others are reset on the way)
             sts32(sb + OFF_HELD, (uint32_t)held);
         }
@@ -1009,7 +1009,11 @@ __global__ void __launch_bounds__(NW * 32, DpxOcc<NW>::value) fsv_fill_dpx_kerne
         __syncthreads();
         if (tid == 0) {
             const bool lazy = C.pool.lazy && C.pool.lazy_min_pages > 0 && T.tb_pages >= C.pool.lazy_min_pages;      // as task_pages decided
-            if (!SEG) pool_free(C.pool, (int)lds32(sb + OFF_HELD), table, lazy ? C.slot_base + (int)blockIdx.x : -1);
+            if (!SEG) {
+                const int held = (int)lds32(sb + OFF_HELD);
+                if (!lazy && pool_may_keep(C.pool, held)) kept = held;      // table[0 .. held) stays with this CTA for its next task
+                else pool_free(C.pool, held, table, lazy ? C.slot_base + (int)blockIdx.x : -1);
+            }
             if (C.timeline) C.timeline[2 * T.orig + 1] = global_ns();
         }
     }

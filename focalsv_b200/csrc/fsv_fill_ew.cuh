@@ -107,14 +107,14 @@ __global__ void __launch_bounds__((NWM + 1) * 32, EwOcc<NWM>::value) fsv_fill_ew
     const uint32_t extSel = DUAL ? 0xB391u : 0x4341u;
     const bool is_ew = warp == NWM;
     int32_t* table = C.page_tables + (int64_t)blockIdx.x * C.max_pages_per_task;
-    int pending = -1;
+    int pending = -1, kept = 0;
     if (tid < 3 * NSLOT) sts32(sb + OFF_MX + 4u * (uint32_t)tid, (uint32_t)INT32_MIN);       // slots of warps that do not exist stay at the minimum
 
     for (;;) {
         __syncthreads();
         if (tid == 0) {
             int held = 0;
-            sts32(sb + OFF_TASK, (uint32_t)next_task(C, P.Q, table, pending, true, held));
+            sts32(sb + OFF_TASK, (uint32_t)next_task(C, P.Q, table, pending, true, held, kept));
             sts32(sb + OFF_HELD, (uint32_t)held);
             // a "stop" of the previous task must not be seen by this one; keys start empty
             for (int j = 0; j < 3; ++j) { sts32(sb + OFF_MX + 4u * (uint32_t)(j * NSLOT), (uint32_t)INT32_MIN); sts32(sb + OFF_KEY + 4u * (uint32_t)j, 0xffffffffu); }
@@ -548,7 +548,9 @@ __global__ void __launch_bounds__((NWM + 1) * 32, EwOcc<NWM>::value) fsv_fill_ew
         __syncthreads();
         if (tid == 0) {
             const bool lazy = C.pool.lazy && C.pool.lazy_min_pages > 0 && T.tb_pages >= C.pool.lazy_min_pages;
-            pool_free(C.pool, (int)lds32(sb + OFF_HELD), table, lazy ? C.slot_base + (int)blockIdx.x : -1);
+            const int held = (int)lds32(sb + OFF_HELD);
+            if (!lazy && pool_may_keep(C.pool, held)) kept = held;      // table[0 .. held) stays with this CTA for its next task
+            else pool_free(C.pool, held, table, lazy ? C.slot_base + (int)blockIdx.x : -1);
             if (C.timeline) C.timeline[2 * T.orig + 1] = global_ns();
         }
     }

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(EXACT_THREADS) fsv_fill_exact_kernel(const Fil
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) { int held_; sh_task = next_task(C, P.Q, table, pending, false, held_); }     // always up front
+        if (tid == 0) { int held_, kept_ = 0; sh_task = next_task(C, P.Q, table, pending, false, held_, kept_); }     // always up front, nothing kept
         __syncthreads();
         const int ti = sh_task;
         if (ti < 0) return;
