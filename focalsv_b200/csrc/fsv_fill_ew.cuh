@@ -31,7 +31,13 @@ namespace fsv {
 #ifndef FSV_EW_OCC6
 #define FSV_EW_OCC6 2
 #endif
-template <int NWM> struct EwOcc { static constexpr int value = NWM == 1 ? 6 : NWM == 2 ? 4 : NWM == 4 ? 2 : NWM == 6 ? FSV_EW_OCC6 : 1; };
+#ifndef FSV_EW_OCC1
+#define FSV_EW_OCC1 6
+#endif
+#ifndef FSV_EW_OCC2
+#define FSV_EW_OCC2 4
+#endif
+template <int NWM> struct EwOcc { static constexpr int value = NWM == 1 ? FSV_EW_OCC1 : NWM == 2 ? FSV_EW_OCC2 : NWM == 4 ? 2 : NWM == 6 ? FSV_EW_OCC6 : 1; };
 
 // One DP cell (a lane of the reference's vector, :26-47, :171-196) in the LOW half of every word: the instruction sequence of
 // dpx_cells for one word.  Returns the traceback byte.
