@@ -123,3 +123,39 @@ def test_identical_and_tiny_eligible_tasks(oracle, aligner):
         _check(oracle, aligner, g)
         g = synth._pack("ewt", "asm5" if dual else "hifiasm", pairs, 100, -1)
         _check(oracle, aligner, g)
+
+
+def test_exclusive_launch_and_lazy_pages(oracle):
+    """The kernel's other launch forms: one CTA per SM (force_excl), and tasks whose traceback pages are taken as the task advances
+    (small pages, so that a 6 kb task already spans more than lazy_min_pages of them) out of a pool that only fits a few tasks."""
+    rng = np.random.default_rng(21)
+    pairs = []
+    for L in (900, 2500, 6000, 6100):
+        ref = synth.random_seq(rng, L)
+        q, _ = synth.plant_svs(rng, ref, 2, max_net=150, max_len=120)
+        pairs.append((synth.mutate(rng, q, 0.01, 0.004, 0.004), ref))
+    al = api.Aligner(0)
+    try:
+        for preset, w in (("hifiasm", 500), ("map-hifi", 751)):
+            from focalsv_b200.presets import PRESETS
+            g = synth._pack("ewx", preset, pairs, w, PRESETS[preset].zdrop)
+            al.set_option("force_excl", 1)
+            b = al.batch(g.scoring, g.qarena, g.tarena, g.tasks)
+            plan = b.plan(); b.close()
+            assert ((plan & _abi.PLAN_EDGE_WARP) != 0).all() and ((plan & _abi.PLAN_EXCLUSIVE) != 0).all()
+            bad, _, _ = compare_group(oracle, al, g)
+            assert not bad, ("exclusive", preset, bad)
+            al.set_option("force_excl", 0)
+        al.set_option("traceback_page_bytes", 65536)
+        al.set_option("traceback_budget_bytes", 400 * 65536)
+        al.set_option("pool_stall_ms", 5000)
+        for lazy in (16, 3):
+            al.set_option("lazy_min_pages", lazy)
+            g = synth._pack("ewl", "hifiasm", pairs * 6, 500, 400)
+            b = al.batch(g.scoring, g.qarena, g.tarena, g.tasks)
+            assert ((b.plan() & _abi.PLAN_EDGE_WARP) != 0).any()
+            b.close()
+            bad, _, _ = compare_group(oracle, al, g)
+            assert not bad, ("lazy", lazy, bad)
+    finally:
+        al.close()
