@@ -58,7 +58,7 @@ struct fsv_ctx {
     int64_t page_bytes = 32ll << 20;
     int64_t segment_min_diags = -1;  // tasks with at least this many antidiagonals are cut into segments (0 = off, -1 = auto:
                                      // those whose chain of antidiagonals would outlast 60 % of the batch's throughput time)
-    int segment_warm_pct = 400;      // cold-start lead of a segment, in percent of the band width (+1024 antidiagonals)
+    int segment_warm_pct = 300;      // cold-start lead of a segment, in percent of the band width (+1024 antidiagonals); a boundary that does not verify costs one segment
     int segment_align_pages = 0;     // 0 = segments are multiples of 1024 antidiagonals (default), 1 = whole traceback pages
     int ew_kernel = 1;               // mainstream tasks run on the edge-warp kernel (fsv_fill_ew.cuh): 1 = those that need up to 4 main warps (bands up to
                                      // about 2 000; seven warps of 128 registers spill, so wider bands stay with fsv_fill_dpx_kernel), 2 = all of them, 0 = none

@@ -142,7 +142,7 @@ int fsv_get_stats(const fsv_ctx* ctx, fsv_stats* out);
  *   "segment_min_diags"       tasks with at least this many antidiagonals are cut into segments that run on separate
  *                             CTAs (0 = off, -1 = auto, the default: tasks whose chain would outlast 60 % of the batch)
  *   "segment_rows"            antidiagonals per segment (0 = auto: 4 x the cold-start lead, whole traceback pages)
- *   "segment_warm_pct"        cold-start lead of a segment in percent of the band width (default 400: 2w to forget the start, 2w more until every lane of the band entered after that; 250 still verifies on the probes, 200 does not)
+ *   "segment_warm_pct"        cold-start lead of a segment in percent of the band width (default 300: 2w to forget the start, w more until most lanes of the band entered after that; a boundary that does not verify is repaired: one segment runs again, so a shorter lead trades cells for repairs)
  *   "segment_pool_pct"        share of the traceback pool the segmented tasks may hold (default 45)
  *   "segment_slots"           1 = long tasks beyond the pool share re-use the static pages of earlier ones in turn (default), 0 = they stay whole
  *   "segment_align_pages"     1 = segments are whole traceback pages (default), 0 = any multiple of 1024 antidiagonals (experiment)

@@ -379,7 +379,7 @@ def test_segmented_long_tasks(oracle, preset, w):
         bad, _, _ = compare_group(oracle, al, g, threads=16)
         assert not bad, bad
         assert al.stats()["segment_fallbacks"] >= (3 if w > 1000 else 0), al.stats()      # (a band of 500 forgets its start within the 1 024 extra rows)
-        al.set_option("segment_warm_pct", 400)
+        al.set_option("segment_warm_pct", 300)
         launches_seg = al.stats()["fill_launches"] - launches_seg
         before = al.stats()["fill_launches"]
         al.set_option("segment_min_diags", 0)               # and the same batch unsegmented
