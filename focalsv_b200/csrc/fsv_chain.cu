@@ -34,20 +34,25 @@ void sketch(const uint8_t* s, int32_t n, int k, int w, std::vector<Mz>& out)
     out.clear();
     if (n < k) return;
     const uint64_t mask = k < 32 ? (1ull << (2 * k)) - 1 : ~0ull;
-    std::vector<Mz> ring((size_t)w);
+    // sliding-window minimum over the last w k-mers as a monotonic queue (O(n) instead of O(n w)): dq[head .. tail) holds the candidates in
+    // order of position with strictly increasing hash from back to front removed, so dq[head] is the smallest hash of the window, leftmost on ties
+    std::vector<Mz> dq((size_t)w + 1);
+    int head = 0, tail = 0;          // ring indices into dq, at most w entries
+    auto at = [&](int i) -> Mz& { return dq[(size_t)(i % (w + 1))]; };
     uint64_t kmer = 0;
     int valid = 0, filled = 0, last_pos = -1;
     for (int32_t i = 0; i < n; ++i) {
-        if (s[i] > 3) { valid = 0; filled = 0; continue; }
+        if (s[i] > 3) { valid = 0; filled = 0; head = tail = 0; continue; }
         kmer = ((kmer << 2) | s[i]) & mask;
         if (++valid < k) continue;
-        ring[(size_t)(filled % w)] = Mz{mix64(kmer), i};
+        const Mz e{mix64(kmer), i};
+        while (tail > head && at(tail - 1).h > e.h) --tail;      // a later k-mer wins only with a strictly smaller hash
+        at(tail) = e; ++tail;
         ++filled;
+        if (at(head).pos <= i - w) ++head;                       // left the window of the last w k-mers
         if (filled < w) continue;
-        int best = 0;
-        for (int j = 1; j < w; ++j)
-            if (ring[(size_t)j].h < ring[(size_t)best].h || (ring[(size_t)j].h == ring[(size_t)best].h && ring[(size_t)j].pos < ring[(size_t)best].pos)) best = j;
-        if (ring[(size_t)best].pos != last_pos) { out.push_back(ring[(size_t)best]); last_pos = ring[(size_t)best].pos; }
+        const Mz& b = at(head);
+        if (b.pos != last_pos) { out.push_back(b); last_pos = b.pos; }
     }
 }
 
@@ -152,23 +157,26 @@ void sketch2(const uint8_t* s, int32_t n, int k, int w, std::vector<Mz2>& out)
     if (n < k) return;
     const uint64_t mask = k < 32 ? (1ull << (2 * k)) - 1 : ~0ull;
     const int shift = 2 * (k - 1);
-    std::vector<Mz2> ring((size_t)w);
+    std::vector<Mz2> dq((size_t)w + 1);                          // monotonic queue, as in sketch()
+    int head = 0, tail = 0;
+    auto at = [&](int i) -> Mz2& { return dq[(size_t)(i % (w + 1))]; };
     uint64_t fw = 0, rv = 0;
     int valid = 0, filled = 0, last_pos = -1;
     for (int32_t i = 0; i < n; ++i) {
-        if (s[i] > 3) { valid = 0; filled = 0; continue; }
+        if (s[i] > 3) { valid = 0; filled = 0; head = tail = 0; continue; }
         fw = ((fw << 2) | s[i]) & mask;
         rv = (rv >> 2) | ((uint64_t)(3 - s[i]) << shift);
         if (++valid < k) continue;
         // a palindromic k-mer has no strand: it takes a slot in the window (so that windows stay w k-mers wide) but never wins
         const bool pal = fw == rv;
-        ring[(size_t)(filled % w)] = Mz2{pal ? ~0ull : mix64(fw < rv ? fw : rv), i, fw < rv ? 0 : 1};
+        const Mz2 e{pal ? ~0ull : mix64(fw < rv ? fw : rv), i, fw < rv ? 0 : 1};
+        while (tail > head && at(tail - 1).h > e.h) --tail;
+        at(tail) = e; ++tail;
         ++filled;
+        if (at(head).pos <= i - w) ++head;
         if (filled < w) continue;
-        int best = 0;
-        for (int j = 1; j < w; ++j)
-            if (ring[(size_t)j].h < ring[(size_t)best].h || (ring[(size_t)j].h == ring[(size_t)best].h && ring[(size_t)j].pos < ring[(size_t)best].pos)) best = j;
-        if (ring[(size_t)best].h != ~0ull && ring[(size_t)best].pos != last_pos) { out.push_back(ring[(size_t)best]); last_pos = ring[(size_t)best].pos; }
+        const Mz2& b = at(head);
+        if (b.h != ~0ull && b.pos != last_pos) { out.push_back(b); last_pos = b.pos; }
     }
 }
 
