@@ -126,6 +126,55 @@ def test_chain_pieces_tile_the_pair_and_isolate_the_svs():
     assert len(pcs) == 1 and tuple(pcs[0]) == (0, 500, 0, 0)
 
 
+
+def _naive_minimizers(s, k, w):
+    """(w, k)-minimizers of the forward strand exactly as fsv_chain.cu defines them (hash mix64 of the 2-bit k-mer, the smallest of every
+    window of w consecutive k-mers, leftmost on ties, windows never span a wildcard), the slow obvious way: end positions of the chosen k-mers."""
+    M = (1 << 64) - 1
+
+    def mix64(x):
+        x ^= x >> 33; x = (x * 0xff51afd7ed558ccd) & M; x ^= x >> 33; x = (x * 0xc4ceb9fe1a85ec53) & M; x ^= x >> 33
+        return x
+    out, run = set(), []            # run: (hash, end position) of the k-mers since the last wildcard
+    valid, kmer, mask = 0, 0, (1 << (2 * k)) - 1
+    for i, c in enumerate(int(x) for x in s):
+        if c > 3:
+            valid, run = 0, []
+            continue
+        kmer = ((kmer << 2) | c) & mask
+        valid += 1
+        if valid < k:
+            continue
+        run.append((mix64(kmer), i))
+        if len(run) >= w:
+            out.add(min(run[-w:])[1])
+    return out
+
+
+def test_piece_boundaries_are_shared_minimizers():
+    """Every cut between two pieces is the END of a k-mer that both sequences share and that is a minimizer of both (what the sketch + anchor
+    join must deliver whatever their implementation: the O(n) monotonic-queue sketch is checked against the obvious O(n w) definition)."""
+    from focalsv_b200 import api
+    rng = np.random.default_rng(5)
+    for (k, w), L in (((19, 19), 6000), ((15, 10), 4000), ((19, 10), 3000)):
+        ref = synth.random_seq(rng, L)
+        q, _ = synth.plant_svs(rng, ref, 3, max_net=600, max_len=500)
+        q = synth.mutate(rng, q, 0.01, 0.003, 0.003)
+        q = q.copy(); q[rng.integers(0, len(q), 4)] = 4                    # a few wildcards: windows restart behind them
+        ref = ref.copy(); ref[L // 2:L // 2 + 120] = 0                      # a homopolymer stretch: ties, leftmost wins
+        pcs, _, n_anchor = api.chain_pieces(q, ref, k, w, 50, 100000, 200)
+        assert n_anchor > 20 and len(pcs) > 5
+        mq, mt = _naive_minimizers(q, k, w), _naive_minimizers(ref, k, w)
+        for pc in pcs[:-1]:                                                # the last piece ends at the sequence ends
+            qe, te = int(pc["q_end"]), int(pc["t_end"])
+            if qe < k or te < k:                                           # (the leading piece before the first anchor starts at its k-mer's first base)
+                continue
+            same = np.array_equal(q[qe - k:qe], ref[te - k:te])
+            if not same:                                                   # the first cut is the START of the first anchor: its k-mer lies behind it
+                assert np.array_equal(q[qe:qe + k], ref[te:te + k]) and (qe + k - 1) in mq and (te + k - 1) in mt, (k, w, qe, te)
+                continue
+            assert (qe - 1) in mq and (te - 1) in mt, (k, w, qe, te)
+
 def test_chained_alignment_is_a_valid_global_alignment_and_recovers_the_svs(oracle):
     windows, contigs, truth = _regions(21, n=3, L=20000)
     recs = hook.realign_regions_chained(_OracleRunner(oracle), windows, contigs, preset="asm5", bw=2000)
